@@ -1,0 +1,164 @@
+"""The oracle (oracle/crossroad_oracle.py) against the golden vectors produced by the
+UNMODIFIED reference source (tests/golden/make_golden.py).  Bit-equality is required:
+both sides do fp32 IEEE element-wise arithmetic with float64-rounded transcendentals,
+so any difference is a transcription error in the oracle's expression trees."""
+import numpy as np
+import pytest
+
+from conftest import TASKS, golden_paths
+from oracle import crossroad_oracle as orc
+
+
+def _same(a, b, what=''):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if a.dtype.kind == 'f':
+        assert a.dtype == b.dtype == np.float32, (what, a.dtype, b.dtype)
+        ok = (a.view(np.int32) == b.view(np.int32)) | (np.isnan(a) & np.isnan(b)) | ((a == 0) & (b == 0))
+        assert ok.all(), (what, int((~ok).sum()), a[~ok][:5], b[~ok][:5])
+    else:
+        assert (a == b).all(), what
+
+
+def test_constants(golden_common):
+    c = golden_common
+    assert (orc.L, orc.W, orc.LANE_WIDTH, orc.LANE_NUMBER, orc.CROSSROAD_SIZE, orc.EXPECTED_V) == \
+        tuple(float(c['const_' + k]) for k in ('L', 'W', 'LANE_WIDTH', 'LANE_NUMBER', 'CROSSROAD_SIZE', 'EXPECTED_V'))
+    for task in TASKS:
+        assert list(c['mode_list_' + task]) == orc.VEHICLE_MODE_LIST[task]
+    for k, v in orc.VEHICLE_PARAMS.items():
+        assert float(c['vp_' + k]) == v
+
+
+def test_f_xu(golden_common):
+    c = golden_common
+    nxt, par = orc.f_xu(c['fxu_states'], c['fxu_actions'], 0.1)
+    _same(nxt, c['fxu_next'], 'f_xu next')
+    _same(par, c['fxu_params'], 'f_xu params')
+    nxt, par = orc.prediction(c['fxu_states'], c['fxu_actions'], 10)
+    _same(nxt, c['pred_next'], 'prediction next')
+    _same(par, c['pred_params'], 'prediction params')
+
+
+def test_f_xu_hand_kat():
+    # straight-line motion at heading 90 deg
+    nxt, par = orc.f_xu(np.array([[5, 0, 0, 0, 0, 90]], np.float32), np.zeros((1, 2), np.float32), 0.1)
+    assert nxt[0, 0] == 5 and nxt[0, 1] == 0 and nxt[0, 2] == 0 and nxt[0, 4] == 0.5 and nxt[0, 5] == 90
+    assert abs(nxt[0, 3] - 0.5 * np.cos(np.float64(np.float32(np.pi) / np.float32(2)))) < 1e-12 + 1e-7 * 2.2e-8
+
+
+def test_action_scaling(golden_common):
+    c = golden_common
+    _same(orc.action_transformation(c['act_norm']), c['act_scaled'])
+    s = orc.action_transformation(np.array([[1, 1], [-1, -1], [2, 0]], np.float32))
+    assert np.allclose(s, [[0.4, 1.5], [-0.4, -3.0], [0.42, -0.75]], atol=1e-6)
+
+
+def test_phi_wrap(golden_common):
+    _same(orc.deal_with_phi_diff(golden_common['phidiff_in']), golden_common['phidiff_out'])
+
+
+def test_predict_for_a_mode(golden_common):
+    c = golden_common
+    for mode in ('dl', 'rd', 'ur', 'lu', 'dr', 'ru', 'ul', 'ld', 'du', 'ud', 'lr', 'rl'):
+        _same(orc.predict_for_a_mode(c['pfm_in'], mode), c['pfm_out_' + mode], mode)
+
+
+def test_gym_helpers(golden_common):
+    c = golden_common
+    for task in TASKS:
+        got = np.array([orc.judge_feasible(x, y, task) for x, y in c['jf_xy']])
+        assert (got == c['jf_' + task]).all()
+    assert [orc.deal_with_phi(float(p)) for p in c['dwp_in']] == list(c['dwp_out'])
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_path_tables(task, golden_task):
+    g = golden_task(task)
+    paths, len_list, ctrl = orc.construct_ref_paths(task)
+    assert (np.array(len_list) == g['path_len_list']).all()
+    assert np.array_equal(np.array(ctrl, dtype=np.float64), g['control_points'])
+    expect_len = dict(left=3657, straight=3897, right=3117)[task]
+    for i, p in enumerate(paths):
+        assert len(p[0]) == expect_len
+        _same(p[0], g['path%d_x' % i], 'x')
+        _same(p[1], g['path%d_y' % i], 'y')
+        # heading: the reference calls NumPy's fp32 arctan2 (build/SIMD dependent last ulp);
+        # the oracle uses float64 atan2 rounded to fp32 (machine independent).  NumPy SVML atan2f
+        # is a <= 4 ulp routine; measured here: max 3 ulp (relative 3.6e-7, far inside rtol 1e-5).
+        a, b = p[2], g['path%d_phi' % i]
+        ulp = np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
+        ulp[(a == 0) & (b == 0)] = 0
+        assert ulp.max() <= 4, (task, i, int(ulp.max()))
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_tracking(task, golden_task):
+    g = golden_task(task)
+    rp = orc.ReferencePath(task, 0, path_list=golden_paths(g))      # the reference's own tables
+    for pi in range(3):
+        rp.set_path(pi)
+        xs, ys, phis, vs = g['trk%d_in' % pi].T
+        for n in (0, 3, 10):
+            _same(rp.tracking_error_vector(xs, ys, phis, vs, n), g['trk%d_n%d' % (pi, n)], 'trk n=%d' % n)
+        idx, pts = rp.find_closest_point(xs, ys)
+        assert (idx == g['fcp%d_idx' % pi]).all()
+        _same(np.stack(pts, 1), g['fcp%d_pts' % pi])
+        idx5, _ = rp.find_closest_point(xs, ys, ratio=5)
+        assert (idx5 == g['fcp%d_idx_r5' % pi]).all()
+        fut = rp.future_n_data(np.array([600, 0, 3500, len(rp.path[0]) - 3], np.int64), 5)
+        _same(np.stack([np.stack(f, 1) for f in fut], 0), g['fut%d' % pi])
+        # on-waypoint poses -> zero tracking error (SURVEY 8c KAT)
+        t0 = rp.tracking_error_vector(xs, ys, phis, vs, 0)
+        assert np.abs(t0[8:12]).max() == 0
+
+
+def test_tracking_reference_script_inputs(golden_task):
+    """The inputs of the reference's test_tracking_error_vector (DM:805-808), task left path 0;
+    expected values from SURVEY 8c (scratch restatement) to 5 decimals."""
+    g = golden_task('left')
+    want = np.array([[-0.32387, -7.79610, 2], [-8.86666, 2.28967, 4], [6.62911, -0.16386, 2], [2.51011, 8.17429, 2]])
+    assert np.allclose(g['trk0_n0'][:4], want, atol=1e-5)
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_compute_rewards(task, golden_task):
+    g = golden_task(task)
+    keys = list(g['rew_dict_keys'])
+    for V in (orc.VEH_NUM[task], 32):
+        ob, an = g['rew_V%d_obs' % V], g['rew_V%d_act' % V]
+        r = orc.compute_rewards(ob, orc.action_transformation(an), task, 0)
+        _same(np.stack(r[:5], 1), g['rew_V%d_out5' % V], 'out5 V=%d' % V)
+        _same(np.stack([r[5][k] for k in keys], 1), g['rew_V%d_dict' % V], 'dict V=%d' % V)
+        assert sorted(orc.REWARD_DICT_KEYS) == keys
+        # pad vehicles far away -> veh2veh exactly zero
+        assert r[3][0] == 0
+        assert (g['rew_V%d_out5' % V][:, 1] > 0).any(), 'synthetic batch should exercise the hinge terms'
+
+
+@pytest.mark.parametrize('task', TASKS)
+@pytest.mark.parametrize('tag', ['cfg1', 'selV', 'trnV', 'sel32', 'trn32', 'seln10', 'trnn3'])
+def test_rollout(task, tag, golden_task):
+    """H=25 free-running rollout_out, bit-exact against the reference (config #1 = 'cfg1')."""
+    g = golden_task(task)
+    ob0, ref, tape = g['ro_%s_obs0' % tag], g['ro_%s_ref' % tag], g['ro_%s_tape' % tag]
+    n = {'seln10': 10, 'trnn3': 3}.get(tag, 0)
+    V = (ob0.shape[1] - 6 - 3 * (n + 1)) // 4
+    mode = 'training' if tag.startswith('trn') else 'selecting'
+    from env_build_b200.synthetic import tiled_mode_list
+    model = orc.EnvironmentModel(task, n, mode=mode, path_list=golden_paths(g),
+                                 veh_mode_list=tiled_mode_list(orc.VEHICLE_MODE_LIST[task], V))
+    if mode == 'training':
+        model.reset(ob0, ref)
+    else:
+        model.add_traj(ob0, int(g['ro_%s_path' % tag]))
+    for t in range(tape.shape[0]):
+        res = model.rollout_out(tape[t])
+        _same(res[0], g['ro_%s_obs' % tag][t], '%s obs t=%d' % (tag, t))
+        _same(np.stack(res[1:], 1), g['ro_%s_out5' % tag][t], '%s out5 t=%d' % (tag, t))
+    if tag in ('selV', 'sel32'):
+        model.add_traj(ob0, int(g['ro_%s_path' % tag]))
+        _same(model.ss(ob0, tape[0], lam=0.1), g['ss_%s' % tag], 'ss')
+    if mode == 'training':
+        # ref_index 3 matches no path -> zero tracking columns (DM:342-353)
+        assert ref[0] == 3 and np.abs(g['ro_%s_obs' % tag][:, 0, 6:9 + 3 * n]).max() == 0
