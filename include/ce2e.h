@@ -1,0 +1,156 @@
+/* ce2e.h -- C ABI of libce2e.so: the CrossroadEnd2end model hot path on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the data-parallel path of idthanm/env_build
+ * (SURVEY.md section 8b).  Every entry point names the reference interface it
+ * replaces; citations are file:line into the reference checkout
+ * (DM = dynamics_and_models.py, E2E = endtoend.py, EU = endtoend_env_utils.py).
+ *
+ * Conventions
+ *   - All tensor pointers are DEVICE pointers to fp32 (or int32/int64 where stated),
+ *     owned by the caller.  The library never allocates or frees caller buffers,
+ *     never synchronises and enqueues all work on `stream` (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream), so every call is CUDA-graph capturable.
+ *   - Observation rows are AoS fp32 with a leading dimension `ld` (floats between
+ *     consecutive rows, ld >= D), BLAS style, so a caller may keep rows padded for
+ *     16-byte alignment of the vehicle block.  Row layout (E2E:300, DM:189-194):
+ *        [v_x v_y r x y phi_deg | d_y d_phi_deg d_v | (dx dy dphi)*n | (x y v phi_deg)*V]
+ *   - Every function returns 0 on success or a negative CE2E_ERR_* code and stores a
+ *     thread-local message readable with ce2e_last_error().
+ *   - Kernels never trap on NaN/Inf; they propagate like the reference's TF ops.
+ *   - fp32 arithmetic follows the reference's expression trees with one rounding per
+ *     op and no FMA contraction; sin/cos/atan are CUDA's
+ *     <= 2 ulp routines.
+ */
+#ifndef CE2E_H_
+#define CE2E_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CE2E_VERSION 100          /* 0.1.0 */
+#define CE2E_MAX_PATHS 4
+#define CE2E_MAX_VEH 256          /* vehicles per observation row */
+
+#define CE2E_OK 0
+#define CE2E_ERR_NULL (-1)        /* required pointer is NULL */
+#define CE2E_ERR_SHAPE (-2)       /* bad B / V / n / ld / length */
+#define CE2E_ERR_TASK (-3)        /* task not in {left, straight, right} (DM:274, DM:668, DM:747 asserts) */
+#define CE2E_ERR_PATH (-4)        /* path index outside the handle's path list */
+#define CE2E_ERR_CUDA (-5)        /* CUDA runtime error (message has the cudaError string) */
+#define CE2E_ERR_NOMEM (-6)
+
+/* training_task of EnvironmentModel / ReferencePath (DM:91, DM:584) */
+#define CE2E_TASK_LEFT 0
+#define CE2E_TASK_STRAIGHT 1
+#define CE2E_TASK_RIGHT 2
+
+/* turn class of one surrounding vehicle = the branch predict_for_a_mode takes (DM:416-421):
+ *  +1 for modes dl, rd, ur, lu;  -1 for dr, ru, ul, ld;  0 otherwise.                  */
+typedef struct ce2e_turn_classes {
+    int8_t tc[CE2E_MAX_VEH];
+} ce2e_turn_classes;
+
+/* Opaque device-resident copy of a task's reference-path tables
+ * (ReferencePath.path_list, DM:584-700).                                                  */
+typedef struct ce2e_paths ce2e_paths;
+
+int ce2e_version(void);
+const char *ce2e_last_error(void);
+
+/* Number of CUDA kernels this library has launched from the calling thread since load. */
+int64_t ce2e_launch_count(void);
+
+/* ReferencePath.__init__ (DM:584-592): upload n_paths tables of HOST fp32 arrays
+ * xs[i], ys[i], phis[i] of length lens[i] (path_list[i], DM:631).  The handle keeps the
+ * full tables plus the every-10th-point copy find_closest_point uses (DM:704-706).
+ * Synchronous (one-time setup).                                                           */
+int ce2e_paths_create(int task, int n_paths, const int32_t *lens, const float *const *xs,
+                      const float *const *ys, const float *const *phis, ce2e_paths **out);
+int ce2e_paths_destroy(ce2e_paths *paths);
+
+/* EnvironmentModel._action_transformation_for_end2end (DM:128-132; NumPy twin E2E:258-267).
+ * act_norm, act_scaled: [B,2] contiguous.                                                 */
+int ce2e_action_transform(const float *act_norm, float *act_scaled, int64_t B, void *stream);
+
+/* VehicleDynamics.f_xu(states, actions, tau) (DM:52-83) / .prediction (DM:85-87).
+ * states [B,6] (ld_states), actions [B,2] contiguous SCALED actions (steer rad, a_x), tau the
+ * Python float the reference passes (rounded to fp32 where TF does),
+ * next [B,6] (ld_next); params [B,4] contiguous = (alpha_f, alpha_r, miu_f, miu_r) or NULL.
+ * clip_vx != 0 additionally applies ego_predict's v_x = clip(v_x, 0, 35) (DM:386-392).     */
+int ce2e_dynamics_step(const float *states, int64_t ld_states, const float *actions, double tau,
+                       float *next, int64_t ld_next, float *params, int clip_vx, int64_t B,
+                       void *stream);
+
+/* ReferencePath.find_closest_point(xs, ys, ratio) (DM:702-715) on path `path_index`:
+ * idx_out [B] int64 = ratio * first-argmin of the squared distance over every ratio-th
+ * waypoint; pts_out [3,B] contiguous = (x, y, phi_deg) of that waypoint (indexs2points,
+ * DM:726-733).  Either output may be NULL.                                                */
+int ce2e_find_closest_point(const ce2e_paths *paths, int path_index, const float *xs,
+                            const float *ys, int ratio, int64_t *idx_out, float *pts_out,
+                            int64_t B, void *stream);
+
+/* ReferencePath.indexs2points (DM:726-733) / future_n_data (DM:717-724).
+ * n_future == 0: pts_out [3,B] = points at clamp(idx).  n_future > 0: pts_out
+ * [n_future,3,B] = the preview points idx+80k clamped to L-2.                              */
+int ce2e_index_points(const ce2e_paths *paths, int path_index, const int64_t *idx, int n_future,
+                      float *pts_out, int64_t B, void *stream);
+
+/* ReferencePath.tracking_error_vector(xs, ys, phis, vs, n) (DM:735-770).
+ * ref_idx == NULL: every row uses path `path_index` (mode != 'training', DM:334-339).
+ * ref_idx != NULL ([B] int32): row i uses path ref_idx[i]; a value outside the path
+ * list yields zeros (mode == 'training', DM:340-353).  out: [B, 3(n+1)] with ld_out.       */
+int ce2e_tracking_error(const ce2e_paths *paths, int path_index, const int32_t *ref_idx,
+                        const float *xs, const float *ys, const float *phis, const float *vs,
+                        int n_future, float *out, int64_t ld_out, int64_t B, void *stream);
+
+/* EnvironmentModel.compute_rewards(obses, actions) (DM:186-320).  actions = SCALED [B,2].
+ * out5 [5,B] contiguous = rewards, punish_term_for_training, real_punish_term,
+ * veh2veh4real, veh2road4real.  dict16 [16,B] or NULL = reward_dict in the key order of
+ * DM:302-318 (punish_steer, punish_a_x, punish_yaw_rate, devi_v, devi_y, devi_phi,
+ * scaled_punish_steer, scaled_punish_a_x, scaled_punish_yaw_rate, scaled_devi_v,
+ * scaled_devi_y, scaled_devi_phi, veh2veh4training, veh2road4training, veh2veh4real,
+ * veh2road4real).                                                                         */
+int ce2e_compute_rewards(int task, const float *obs, int64_t ld, const float *actions, int V,
+                         int n_future, float *out5, float *dict16, int64_t B, void *stream);
+
+/* EnvironmentModel.compute_next_obses(obses, actions) (DM:322-358): the next-observation half
+ * of ce2e_rollout_step on its own; actions = SCALED [B,2].                                 */
+int ce2e_compute_next_obses(const ce2e_paths *paths, int path_index, const int32_t *ref_idx,
+                            const float *obs_in, int64_t ld_in, const float *actions,
+                            const ce2e_turn_classes *turn, int V_in, int V_out, int n_future,
+                            float *obs_out, int64_t ld_out, int64_t B, void *stream);
+
+/* EnvironmentModel.veh_predict (DM:394-427): veh_in/veh_out point at the first vehicle
+ * column of each row ([B,4V] with ld_in / ld_out).                                        */
+int ce2e_veh_predict(const float *veh_in, int64_t ld_in, const ce2e_turn_classes *turn, int V,
+                     float *veh_out, int64_t ld_out, int64_t B, void *stream);
+
+/* EnvironmentModel.rollout_out(actions) (DM:118-126), one fused launch:
+ *   action scaling (DM:128-132) -> compute_rewards on obs_in (DM:186-320) ->
+ *   compute_next_obses (DM:322-358) = ego_predict + tracking_error_vector on the row's
+ *   path + veh_predict.
+ * obs_in [B, 6+3(n+1)+4*V_in] (ld_in); obs_out [B, 6+3(n+1)+4*V_out] (ld_out), V_out <= V_in
+ * (the reference predicts only len(VEHICLE_MODE_LIST[task]) vehicles, DM:398-402; pass
+ * V_out = V_in with a length-V_in turn list for the general case).  obs_out must not
+ * overlap obs_in.  act_norm [B,2] in [-1,1]; ref_idx/path_index as in ce2e_tracking_error;
+ * out5 [5,B] as in ce2e_compute_rewards; act_scaled_out [B,2] or NULL receives
+ * self.actions (DM:120).                                                                  */
+int ce2e_rollout_step(const ce2e_paths *paths, int path_index, const int32_t *ref_idx,
+                      const float *obs_in, int64_t ld_in, const float *act_norm,
+                      const ce2e_turn_classes *turn, int V_in, int V_out, int n_future,
+                      float *obs_out, int64_t ld_out, float *out5, float *act_scaled_out,
+                      int64_t B, void *stream);
+
+/* EnvironmentModel.ss(obses, actions, lam) (DM:134-184): discrete barrier penalty.
+ * obs/next_obs [B,D] rows with V vehicles each (next_obs from ce2e_rollout_step or
+ * compute_next_obses); out [B].                                                           */
+int ce2e_ss(const float *obs, int64_t ld, const float *next_obs, int64_t ld_next, int V,
+            int n_future, double lam, float *out, int64_t B, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CE2E_H_ */

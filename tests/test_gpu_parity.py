@@ -1,0 +1,419 @@
+"""CUDA path (libce2e.so through env_build_b200's reference-shaped API) against the oracle and
+the golden vectors generated from the unmodified reference.  Needs a GPU.
+
+Tolerances: integer / index results and every function without a transcendental
+(find_closest_point, tracking_error_vector, action scaling, indexs2points) must be BIT-EXACT;
+functions through sin/cos/atan (f_xu, compute_rewards, veh_predict, rollout_out) must satisfy
+allclose(rtol=1e-5, atol=1e-5) -- the tolerance BASELINE.json's north_star states.
+Rows whose nearest-waypoint decision is a near-tie in the oracle (margin between the best and
+second-best squared distance < 1e-4 m^2) are excluded from next-obs tracking comparisons: a
+1-ulp difference in sin/cos can legitimately move such a row to the neighbouring waypoint."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TASKS, golden_paths
+from oracle import crossroad_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = ATOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def dm():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from env_build_b200 import _lib
+    if _lib.needs_build():
+        _lib.build()
+    from env_build_b200 import dynamics_and_models
+    return dynamics_and_models
+
+
+def bits_equal(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype == np.float32, (a.shape, b.shape, a.dtype, b.dtype)
+    ok = (a.view(np.int32) == b.view(np.int32)) | ((a == 0) & (b == 0)) | (np.isnan(a) & np.isnan(b))
+    assert ok.all(), (int((~ok).sum()), a[~ok][:5], b[~ok][:5])
+
+
+def close(a, b, what=''):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    bad = ~np.isclose(a, b, rtol=RTOL, atol=ATOL, equal_nan=True)
+    assert not bad.any(), (what, int(bad.sum()), a[bad][:5], b[bad][:5], float(np.abs(a - b)[bad].max()))
+
+
+def tiled(task, V):
+    from env_build_b200.synthetic import tiled_mode_list
+    return tiled_mode_list(orc.VEHICLE_MODE_LIST[task], V)
+
+
+# ------------------------------------------------------------------------------------------
+# VehicleDynamics
+# ------------------------------------------------------------------------------------------
+def test_f_xu_golden(dm, golden_common):
+    c = golden_common
+    vd = dm.VehicleDynamics()
+    nxt, par = vd.f_xu(c['fxu_states'], c['fxu_actions'], 0.1)
+    close(nxt.numpy(), c['fxu_next'], 'f_xu next')
+    close(par.numpy(), c['fxu_params'], 'f_xu params')
+    nxt, par = vd.prediction(c['fxu_states'], c['fxu_actions'], 10)
+    close(nxt.numpy(), c['pred_next'], 'prediction')
+    # everything except x', y' (the only columns through sin/cos) is plain IEEE arithmetic
+    bits_equal(nxt.numpy()[:, [0, 1, 2, 5]], c['pred_next'][:, [0, 1, 2, 5]])
+    assert vd.vehicle_params['F_zf'] == float(c['vp_F_zf']) and vd.vehicle_params['F_zr'] == float(c['vp_F_zr'])
+
+
+def test_dynamics_config2(dm):
+    """BASELINE config #2: batch=4096 ego-only dynamics step."""
+    rng = np.random.default_rng(20210312)
+    B = 4096
+    st = np.stack([rng.uniform(0, 12, B), rng.uniform(-1, 1, B), rng.uniform(-0.5, 0.5, B), rng.uniform(-60, 60, B),
+                   rng.uniform(-60, 60, B), rng.uniform(-180, 180, B)], 1).astype(np.float32)
+    st[:16, 0] = 0.0                                   # standstill rows (no singularity, DM:76/78)
+    ac = orc.action_transformation(rng.uniform(-1.2, 1.2, (B, 2)).astype(np.float32))
+    want, wpar = orc.f_xu(st, ac, 0.1)
+    got, gpar = dm.VehicleDynamics().f_xu(st, ac, 0.1)
+    close(got.numpy(), want)
+    bits_equal(got.numpy()[:, [0, 1, 2, 5]], want[:, [0, 1, 2, 5]])
+    ok = st[:, 0] > 0.05                               # alpha = atan(./(v_x+1e-8)) is ill-conditioned at rest
+    close(gpar.numpy()[ok], wpar[ok])
+    close(gpar.numpy()[:, 2:], wpar[:, 2:])
+    # hand KAT: heading 90 deg, no action
+    n, _ = dm.VehicleDynamics().f_xu(np.array([[5, 0, 0, 0, 0, 90]], np.float32), np.zeros((1, 2), np.float32), 0.1)
+    n = n.numpy()[0]
+    assert n[0] == 5 and n[1] == 0 and n[2] == 0 and n[4] == 0.5 and n[5] == 90 and abs(n[3] + 2.1856e-8) < 1e-9
+
+
+def test_action_scaling(dm, golden_common):
+    m = dm.EnvironmentModel('left')
+    bits_equal(m._action_transformation_for_end2end(golden_common['act_norm']).numpy(), golden_common['act_scaled'])
+
+
+def test_phi_wrap(dm, golden_common):
+    bits_equal(dm.deal_with_phi_diff(golden_common['phidiff_in']).numpy(), golden_common['phidiff_out'])
+
+
+# ------------------------------------------------------------------------------------------
+# ReferencePath
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('task', TASKS)
+def test_tracking_golden(dm, task, golden_task):
+    g = golden_task(task)
+    rp = dm.ReferencePath(task, 0, path_list=golden_paths(g))          # the reference's own tables
+    for pi in range(3):
+        rp.set_path(pi)
+        xs, ys, phis, vs = (np.ascontiguousarray(c) for c in g['trk%d_in' % pi].T)
+        for n in (0, 3, 10):
+            bits_equal(rp.tracking_error_vector(xs, ys, phis, vs, n).numpy(), g['trk%d_n%d' % (pi, n)])
+        idx, pts = rp.find_closest_point(xs, ys)
+        assert idx.dtype == torch.int64 and (idx.numpy() == g['fcp%d_idx' % pi]).all()
+        bits_equal(np.stack([p.numpy() for p in pts], 1), g['fcp%d_pts' % pi])
+        idx5, _ = rp.find_closest_point(xs, ys, ratio=5)
+        assert (idx5.numpy() == g['fcp%d_idx_r5' % pi]).all()
+        fut = rp.future_n_data(np.array([600, 0, 3500, len(rp.path[0]) - 3], np.int64), 5)
+        bits_equal(np.stack([np.stack([c.numpy() for c in f], 1) for f in fut], 0), g['fut%d' % pi])
+        pts2 = rp.indexs2points(np.array([-5, 0, 17, 10 ** 6], np.int64))
+        want = orc.ReferencePath(task, pi, path_list=golden_paths(g)).indexs2points(np.array([-5, 0, 17, 10 ** 6]))
+        bits_equal(np.stack([p.numpy() for p in pts2]), np.stack(want))
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_tracking_random_bit_exact(dm, task):
+    """Own tables, 20k random poses over the whole map (incl. far outside), per-row paths."""
+    rng = np.random.default_rng(5)
+    B = 20000
+    rp = dm.ReferencePath(task, 0)
+    xs = rng.uniform(-80, 80, B).astype(np.float32)
+    ys = rng.uniform(-80, 80, B).astype(np.float32)
+    phis = rng.uniform(-360, 360, B).astype(np.float32)
+    vs = rng.uniform(0, 35, B).astype(np.float32)
+    ref = rng.integers(-1, 5, B).astype(np.int32)
+    got = rp.tracking_error_vector(xs, ys, phis, vs, 4, ref_indexes=ref).numpy()
+    want = np.zeros_like(got)
+    for pi in range(3):
+        o = orc.ReferencePath(task, pi, path_list=rp.path_list)
+        m = ref == pi
+        want[m] = o.tracking_error_vector(xs[m], ys[m], phis[m], vs[m], 4)
+    bits_equal(got, want)
+    assert np.abs(got[(ref < 0) | (ref > 2)]).max() == 0
+
+
+# ------------------------------------------------------------------------------------------
+# EnvironmentModel pieces
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('task', TASKS)
+def test_compute_rewards_golden(dm, task, golden_task):
+    g = golden_task(task)
+    keys = list(g['rew_dict_keys'])
+    for V in (orc.VEH_NUM[task], 32):
+        m = dm.EnvironmentModel(task, veh_mode_list=tiled(task, V))
+        ob, an = g['rew_V%d_obs' % V], g['rew_V%d_act' % V]
+        res = m.compute_rewards(ob, m._action_transformation_for_end2end(an))
+        close(np.stack([r.numpy() for r in res[:5]], 1), g['rew_V%d_out5' % V], 'out5 V=%d' % V)
+        close(np.stack([res[5][k].numpy() for k in keys], 1), g['rew_V%d_dict' % V], 'dict V=%d' % V)
+        assert sorted(res[5].keys()) == keys
+        want = g['rew_V%d_out5' % V]
+        # zero stays exactly zero (callers test `punish > 0`, hier_decision.py:97)
+        got = np.stack([r.numpy() for r in res[:5]], 1)
+        assert ((got[:, 1:] == 0) == (want[:, 1:] == 0)).all()
+
+
+def test_predict_for_a_mode_golden(dm, golden_common):
+    c = golden_common
+    m = dm.EnvironmentModel('left')
+    for mode in ('dl', 'rd', 'ur', 'lu', 'dr', 'ru', 'ul', 'ld', 'du', 'ud', 'lr', 'rl'):
+        got = m.predict_for_a_mode(c['pfm_in'], mode).numpy()
+        close(got, c['pfm_out_' + mode], mode)
+        bits_equal(got[:, 2:], c['pfm_out_' + mode][:, 2:])        # v and phi: no sin/cos involved
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_veh_and_ego_predict(dm, task):
+    rng = np.random.default_rng(11)
+    from env_build_b200 import synthetic as syn
+    m = dm.EnvironmentModel(task)
+    V = orc.VEH_NUM[task]
+    obs = syn.make_obs(rng, 777, task, V, m.ref_path.path_list, 0)
+    close(m.veh_predict(obs[:, 9:]).numpy(), orc.veh_predict(obs[:, 9:], orc.VEHICLE_MODE_LIST[task]))
+    act = orc.action_transformation(syn.make_actions(rng, 1, 777)[0])
+    close(m.ego_predict(obs[:, :6], act).numpy(), orc.ego_predict(obs[:, :6], act))
+
+
+# ------------------------------------------------------------------------------------------
+# rollout_out
+# ------------------------------------------------------------------------------------------
+ROLLOUT_TAGS = ['cfg1', 'selV', 'trnV', 'sel32', 'trn32', 'seln10', 'trnn3']
+
+
+def _models(dm, g, task, tag):
+    ob0 = g['ro_%s_obs0' % tag]
+    n = {'seln10': 10, 'trnn3': 3}.get(tag, 0)
+    V = (ob0.shape[1] - 6 - 3 * (n + 1)) // 4
+    mode = 'training' if tag.startswith('trn') else 'selecting'
+    model = dm.EnvironmentModel(task, n, mode=mode, veh_mode_list=tiled(task, V))
+    model.ref_path = dm.ReferencePath(task, 0, path_list=golden_paths(g))
+    om = orc.EnvironmentModel(task, n, mode=mode, path_list=golden_paths(g), veh_mode_list=tiled(task, V))
+    return model, om, mode, n
+
+
+@pytest.mark.parametrize('task', TASKS)
+@pytest.mark.parametrize('tag', ROLLOUT_TAGS)
+def test_rollout_teacher_forced(dm, task, tag, golden_task):
+    """Every step of the golden H=25 rollouts, re-seeded from the reference's own obs_t."""
+    g = golden_task(task)
+    model, om, mode, n = _models(dm, g, task, tag)
+    ref, tape = g['ro_%s_ref' % tag], g['ro_%s_tape' % tag]
+    ntr = 3 * (n + 1)
+    prev = g['ro_%s_obs0' % tag]
+    for t in range(tape.shape[0]):
+        if mode == 'training':
+            model.reset(prev, ref)
+            om.reset(prev, ref)
+        else:
+            model.add_traj(prev, int(g['ro_%s_path' % tag]))
+            om.add_traj(prev, int(g['ro_%s_path' % tag]))
+        res = model.rollout_out(tape[t])
+        want_obs, want5 = g['ro_%s_obs' % tag][t], g['ro_%s_out5' % tag][t]
+        _, margin = om.compute_next_obses(prev, orc.action_transformation(tape[t]), return_margin=True)
+        got = res[0].numpy()
+        close(np.stack([r.numpy() for r in res[1:]], 1), want5, '%s out5 t=%d' % (tag, t))
+        close(got[:, :6], want_obs[:, :6], 'ego')
+        close(got[:, 6 + ntr:], want_obs[:, 6 + ntr:], 'veh')
+        ok = margin > 1e-4
+        close(got[ok, 6:6 + ntr], want_obs[ok, 6:6 + ntr], 'tracking')
+        close(model.actions.numpy(), orc.action_transformation(tape[t]))
+        prev = want_obs
+    if mode == 'training':
+        assert ref[0] == 3 and np.abs(got[0, 6:6 + ntr]).max() == 0     # unmatched ref_index -> zeros
+
+
+@pytest.mark.parametrize('task', TASKS)
+@pytest.mark.parametrize('tag', ['selV', 'trn32'])
+def test_rollout_free_running(dm, task, tag, golden_task):
+    """Free-running H=25 (state fed back on the device): drift stays far below the 0.33 m
+    waypoint granularity unless a near-tie flips; reports the max error."""
+    g = golden_task(task)
+    model, om, mode, n = _models(dm, g, task, tag)
+    ref, tape = g['ro_%s_ref' % tag], g['ro_%s_tape' % tag]
+    if mode == 'training':
+        model.reset(g['ro_%s_obs0' % tag], ref)
+    else:
+        model.add_traj(g['ro_%s_obs0' % tag], int(g['ro_%s_path' % tag]))
+    worst = 0.0
+    for t in range(tape.shape[0]):
+        res = model.rollout_out(tape[t])
+        want = g['ro_%s_obs' % tag][t]
+        got = res[0].numpy()
+        worst = max(worst, float(np.abs(got[:, :6] - want[:, :6]).max()))
+        assert np.allclose(got[:, :6], want[:, :6], rtol=1e-4, atol=1e-4)
+        assert np.allclose(got[:, 9 + 3 * n:], want[:, 9 + 3 * n:], rtol=1e-4, atol=1e-4)
+    print('free-running max |ego err| over 25 steps: %.3g' % worst)
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_ss_golden(dm, task, golden_task):
+    g = golden_task(task)
+    for tag in ('selV', 'sel32'):
+        model, om, mode, n = _models(dm, g, task, tag)
+        model.add_traj(g['ro_%s_obs0' % tag], int(g['ro_%s_path' % tag]))
+        got = model.ss(g['ro_%s_obs0' % tag], g['ro_%s_tape' % tag][0], lam=0.1).numpy()
+        close(got, g['ss_%s' % tag], 'ss')
+
+
+@pytest.mark.parametrize('task', TASKS)
+@pytest.mark.parametrize('mode', ['selecting', 'training'])
+@pytest.mark.parametrize('V', [0, 5, 9, 32, 40])
+def test_rollout_synthetic(dm, task, mode, V):
+    """Seeded synthetic batch (ragged size, edge rows, near vehicles) against the oracle."""
+    from env_build_b200 import synthetic as syn
+    rng = np.random.default_rng(20210313 + V)
+    B = 3001
+    model = dm.EnvironmentModel(task, mode=mode, veh_mode_list=tiled(task, V))
+    ref = syn.make_ref_indexes(rng, B, out_of_range_frac=0.03)
+    obs = syn.make_obs(rng, B, task, V, model.ref_path.path_list, ref if mode == 'training' else 2)
+    act = syn.make_actions(rng, 1, B)[0]
+    om = orc.EnvironmentModel(task, mode=mode, path_list=model.ref_path.path_list, veh_mode_list=tiled(task, V))
+    if mode == 'training':
+        model.reset(obs, ref)
+        om.reset(obs, ref)
+    else:
+        model.add_traj(obs, 2)
+        om.add_traj(obs, 2)
+    res = model.rollout_out(act)
+    sc = orc.action_transformation(act)
+    want5 = orc.compute_rewards(obs, sc, task)[:5]
+    want, margin = om.compute_next_obses(obs, sc, return_margin=True)
+    got = res[0].numpy()
+    for a, b in zip(res[1:], want5):
+        close(a.numpy(), b)
+    close(got[:, :6], want[:, :6])
+    close(got[:, 9:], want[:, 9:])
+    ok = margin > 1e-4
+    assert ok.mean() > 0.99
+    close(got[ok, 6:9], want[ok, 6:9])
+    # the separately callable halves agree bit-for-bit with the fused step
+    r5 = model.compute_rewards(obs, sc)[:5]
+    for a, b in zip(res[1:], r5):
+        bits_equal(a.numpy(), b.numpy())
+    if mode == 'training':
+        model.reset(obs, ref)
+    else:
+        model.add_traj(obs, 2)
+    bits_equal(model.compute_next_obses(obs, sc).numpy(), got)
+
+
+def test_rollout_drops_unlisted_vehicles(dm):
+    """DM:398-402: only len(VEHICLE_MODE_LIST[task]) vehicles are predicted, rewards use all."""
+    from env_build_b200 import synthetic as syn
+    rng = np.random.default_rng(3)
+    task, B = 'right', 257
+    model = dm.EnvironmentModel(task, mode='selecting')                 # native list: 5 vehicles
+    obs = syn.make_obs(rng, B, task, 8, model.ref_path.path_list, 0)
+    act = syn.make_actions(rng, 1, B)[0]
+    model.add_traj(obs, 0)
+    res = model.rollout_out(act)
+    om = orc.EnvironmentModel(task, mode='selecting', path_list=model.ref_path.path_list)
+    om.add_traj(obs, 0)
+    want = om.rollout_out(act)
+    assert res[0].shape == (B, 29) == want[0].shape
+    close(res[0].numpy()[:, :6], want[0][:, :6])
+    close(res[0].numpy()[:, 9:], want[0][:, 9:])
+    for a, b in zip(res[1:], want[1:]):
+        close(a.numpy(), b)
+
+
+# ------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE sizes
+# ------------------------------------------------------------------------------------------
+def test_full_size_properties(dm):
+    """B=65536, V=32 (config #3): results do not depend on how the batch is split (the kernel picks
+    a different lanes-per-row factor for small batches), nor on row padding; far vehicles give
+    exactly zero collision penalty."""
+    from env_build_b200 import synthetic as syn
+    rng = np.random.default_rng(20210313)
+    task, B, V = 'left', 65536, 32
+    model = dm.EnvironmentModel(task, mode='training', veh_mode_list=tiled(task, V))
+    ref = syn.make_ref_indexes(rng, B, out_of_range_frac=0.01)
+    obs = syn.make_obs(rng, B, task, V, model.ref_path.path_list, ref)
+    act = syn.make_actions(rng, 1, B)[0]
+    model.reset(obs, ref)
+    full = [r.numpy() for r in model.rollout_out(act)]
+    # (a) shard invariance: 3 ragged shards, concatenated
+    cuts = [0, 1000, 30001, B]
+    parts = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        model.reset(obs[a:b], ref[a:b])
+        parts.append([r.numpy() for r in model.rollout_out(act[a:b])])
+    for i in range(6):
+        bits_equal(np.concatenate([p[i] for p in parts]), full[i])
+    # (b) unpadded rows straight through the C ABI (scalar vehicle loads) == padded rows
+    from env_build_b200 import _lib
+    import ctypes
+    dev_obs = torch.as_tensor(obs[:5001], device='cuda').contiguous()
+    assert dev_obs.stride(0) == 137
+    out = torch.empty((5001, 137), device='cuda')
+    out5 = torch.empty((5, 5001), device='cuda')
+    dact = torch.as_tensor(act[:5001], device='cuda')
+    dref = torch.as_tensor(ref[:5001], device='cuda')
+    _lib.check(_lib.load().ce2e_rollout_step(model.ref_path.handle, 0, dref.data_ptr(), dev_obs.data_ptr(), 137,
+                                             dact.data_ptr(), ctypes.byref(model._turn), V, V, 0, out.data_ptr(), 137,
+                                             out5.data_ptr(), None, 5001, None))
+    torch.cuda.synchronize()
+    model.reset(obs[:5001], ref[:5001])
+    pad = [r.numpy() for r in model.rollout_out(act[:5001])]
+    bits_equal(out.cpu().numpy(), pad[0])
+    bits_equal(out5.cpu().numpy(), np.stack(pad[1:]))
+    # (c) all vehicles far away -> veh2veh exactly 0
+    far = obs.copy()
+    far[:, 9::4] = 500.0
+    model.reset(far, ref)
+    res = model.rollout_out(act)
+    assert float(res[4].abs().max()) == 0.0
+    # (d) statistical sanity against the oracle on a 4096-row sample
+    sel = rng.choice(B, 4096, replace=False)
+    want5 = orc.compute_rewards(obs[sel], orc.action_transformation(act[sel]), task)[:5]
+    for a, b in zip(full[1:], want5):
+        close(a[sel], b)
+
+
+def test_edge_cases_and_errors(dm):
+    m = dm.EnvironmentModel('straight', mode='selecting')
+    m.ref_path.set_path(0)
+    # empty batch
+    m.add_traj(np.zeros((0, 45), np.float32), 0)
+    res = m.rollout_out(np.zeros((0, 2), np.float32))
+    assert res[0].shape == (0, 45) and res[1].shape == (0,)
+    # batch of one (reference callers: hier_decision.py:101)
+    from env_build_b200 import synthetic as syn
+    rng = np.random.default_rng(1)
+    obs = syn.make_obs(rng, 1, 'straight', 9, m.ref_path.path_list, 0)
+    m.add_traj(obs, 0)
+    res = m.rollout_out(np.array([[0.5, 0.0]], np.float32))
+    om = orc.EnvironmentModel('straight', mode='selecting', path_list=m.ref_path.path_list)
+    om.add_traj(obs, 0)
+    want = om.rollout_out(np.array([[0.5, 0.0]], np.float32))
+    close(res[0].numpy(), want[0])
+    assert len(res[0]) == 1 and res[1].numpy()[0] == pytest.approx(float(want[1][0]), rel=1e-5)
+    # error behaviour
+    with pytest.raises(AssertionError):
+        dm.ReferencePath('u-turn')
+    with pytest.raises(ValueError):
+        m.add_traj(np.zeros((4, 44), np.float32), 0)
+    with pytest.raises(ValueError):
+        m.add_traj(obs, 0)
+        m.rollout_out(np.zeros((2, 2), np.float32))
+    with pytest.raises(IndexError):
+        m.add_traj(obs, 7)
+    mt = dm.EnvironmentModel('left', mode='training')
+    mt.reset(np.zeros((2, 41), np.float32))
+    with pytest.raises(ValueError):
+        mt.rollout_out(np.zeros((2, 2), np.float32))
+    # NaN propagates, nothing traps
+    bad = obs.copy()
+    bad[0, 3] = np.nan
+    m.add_traj(bad, 0)
+    r = m.rollout_out(np.array([[0.0, 0.0]], np.float32))
+    assert np.isnan(r[0].numpy()[0, 3])
