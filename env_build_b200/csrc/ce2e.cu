@@ -584,6 +584,7 @@ int model_step_common(const ce2e_paths *paths, int task, int path_index, const i
                     CE2E_MAX_VEH);
     if (n_future < 0 || n_future > 1024) return fail(CE2E_ERR_SHAPE, "bad num_future_data %d", n_future);
     const int D_in = 6 + 3 * (n_future + 1) + 4 * V_in, D_out = 6 + 3 * (n_future + 1) + 4 * V_out;
+    if (B == 0) return CE2E_OK;                   // empty batch: nothing to read or write
     if (!obs_in || !act) return fail(CE2E_ERR_NULL, "obs_in / actions is NULL");
     if (ld_in < D_in) return fail(CE2E_ERR_SHAPE, "ld_in=%lld < D=%d", (long long)ld_in, D_in);
     StepParams P;
@@ -605,7 +606,6 @@ int model_step_common(const ce2e_paths *paths, int task, int path_index, const i
         P.pv.n_paths = 0;
         P.pv.stride = 0;
     }
-    if (B == 0) return CE2E_OK;
     P.dyn = make_dyn_consts(1.0 / 10.0);          // prediction(..., base_frequency = 10.), DM:387
     P.obs_in = obs_in; P.obs_out = obs_out; P.act = act; P.ref_idx = ref_idx; P.out5 = out5;
     P.dict16 = dict16; P.act_scaled_out = act_scaled_out;
@@ -697,8 +697,8 @@ int ce2e_paths_destroy(ce2e_paths *h) {
 int ce2e_action_transform(const float *act_norm, float *act_scaled, int64_t B, void *stream) {
     int rc;
     if ((rc = check_batch(B))) return rc;
-    if (!act_norm || !act_scaled) return fail(CE2E_ERR_NULL, "NULL argument");
     if (B == 0) return CE2E_OK;
+    if (!act_norm || !act_scaled) return fail(CE2E_ERR_NULL, "NULL argument");
     k_action<<<blocks_for(B, 256), 256, 0, (cudaStream_t)stream>>>(act_norm, act_scaled, B);
     return after_launch("k_action");
 }
@@ -708,10 +708,10 @@ int ce2e_dynamics_step(const float *states, int64_t ld_states, const float *acti
                        void *stream) {
     int rc;
     if ((rc = check_batch(B))) return rc;
+    if (B == 0) return CE2E_OK;
     if (!states || !actions || !next) return fail(CE2E_ERR_NULL, "NULL argument");
     if (ld_states < 6 || ld_next < 6) return fail(CE2E_ERR_SHAPE, "ld < 6");
     if (params && !aligned16(params)) return fail(CE2E_ERR_SHAPE, "params must be 16 B aligned");
-    if (B == 0) return CE2E_OK;
     const DynConsts K = make_dyn_consts(tau);
     k_dynamics_step<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
         K, states, ld_states, actions, next, ld_next, params, clip_vx, B);
@@ -723,11 +723,11 @@ int ce2e_find_closest_point(const ce2e_paths *paths, int path_index, const float
                             int64_t B, void *stream) {
     int rc;
     if ((rc = check_batch(B))) return rc;
+    if (B == 0) return CE2E_OK;
     if (!paths || !xs || !ys) return fail(CE2E_ERR_NULL, "NULL argument");
     if (path_index < 0 || path_index >= paths->n_paths)
         return fail(CE2E_ERR_PATH, "path_index %d outside [0, %d)", path_index, paths->n_paths);
     if (ratio < 1) return fail(CE2E_ERR_SHAPE, "ratio %d < 1", ratio);
-    if (B == 0) return CE2E_OK;
     k_closest<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
         paths->full[path_index], paths->L[path_index], ratio, xs, ys, idx_out, pts_out, B);
     return after_launch("k_closest");
@@ -737,11 +737,11 @@ int ce2e_index_points(const ce2e_paths *paths, int path_index, const int64_t *id
                       float *pts_out, int64_t B, void *stream) {
     int rc;
     if ((rc = check_batch(B))) return rc;
+    if (B == 0) return CE2E_OK;
     if (!paths || !idx || !pts_out) return fail(CE2E_ERR_NULL, "NULL argument");
     if (path_index < 0 || path_index >= paths->n_paths)
         return fail(CE2E_ERR_PATH, "path_index %d outside [0, %d)", path_index, paths->n_paths);
     if (n_future < 0) return fail(CE2E_ERR_SHAPE, "n_future < 0");
-    if (B == 0) return CE2E_OK;
     k_index_points<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
         paths->full[path_index], paths->L[path_index], idx, n_future, pts_out, B);
     return after_launch("k_index_points");
@@ -752,11 +752,11 @@ int ce2e_tracking_error(const ce2e_paths *paths, int path_index, const int32_t *
                         int n_future, float *out, int64_t ld_out, int64_t B, void *stream) {
     int rc;
     if ((rc = check_batch(B))) return rc;
+    if (B == 0) return CE2E_OK;
     if (!paths || !xs || !ys || !phis || !vs || !out) return fail(CE2E_ERR_NULL, "NULL argument");
     if (!ref_idx && (path_index < 0 || path_index >= paths->n_paths))
         return fail(CE2E_ERR_PATH, "path_index %d outside [0, %d)", path_index, paths->n_paths);
     if (n_future < 0 || ld_out < 3 * (n_future + 1)) return fail(CE2E_ERR_SHAPE, "bad n_future / ld_out");
-    if (B == 0) return CE2E_OK;
     k_tracking<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
         make_view(paths), paths->task, path_index, ref_idx, xs, ys, phis, vs, n_future, out, ld_out, B);
     return after_launch("k_tracking");
@@ -793,10 +793,11 @@ int ce2e_veh_predict(const float *veh_in, int64_t ld_in, const ce2e_turn_classes
                      float *veh_out, int64_t ld_out, int64_t B, void *stream) {
     int rc;
     if ((rc = check_batch(B))) return rc;
+    if (B == 0) return CE2E_OK;
     if (!veh_in || !veh_out || !turn) return fail(CE2E_ERR_NULL, "NULL argument");
     if (V < 0 || V > CE2E_MAX_VEH || ld_in < 4 * V || ld_out < 4 * V)
         return fail(CE2E_ERR_SHAPE, "bad V=%d / ld", V);
-    if (B == 0 || V == 0) return CE2E_OK;
+    if (V == 0) return CE2E_OK;
     k_veh_predict<<<blocks_for(B * V, 256), 256, 0, (cudaStream_t)stream>>>(veh_in, ld_in, *turn, V,
                                                                              veh_out, ld_out, B);
     return after_launch("k_veh_predict");
@@ -806,10 +807,10 @@ int ce2e_ss(const float *obs, int64_t ld, const float *next_obs, int64_t ld_next
             int n_future, double lam, float *out, int64_t B, void *stream) {
     int rc;
     if ((rc = check_batch(B))) return rc;
+    if (B == 0) return CE2E_OK;
     if (!obs || !next_obs || !out) return fail(CE2E_ERR_NULL, "NULL argument");
     const int D = 6 + 3 * (n_future + 1) + 4 * V;
     if (V < 0 || n_future < 0 || ld < D || ld_next < D) return fail(CE2E_ERR_SHAPE, "bad V / n_future / ld");
-    if (B == 0) return CE2E_OK;
     k_ss<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
         obs, ld, next_obs, ld_next, V, 6 + 3 * (n_future + 1), (float)(1.0 - lam), out, B);
     return after_launch("k_ss");

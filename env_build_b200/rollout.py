@@ -1,0 +1,88 @@
+"""Graph-captured multi-step rollouts on static device buffers.
+
+`EnvironmentModel.rollout_out` allocates its outputs per call like the reference does.  For
+launch-bound inner loops (the reference's shield rollouts: hier_decision.py:89-97, H=5;
+multi_ego.py:187-197, H=20; MPC horizon 25, mpc_ipopt.py:330) `RolloutGraph` keeps the
+observation ping-pong buffers, the action tape and the per-step outputs resident and replays
+the H fused `ce2e_rollout_step` launches as ONE CUDA graph.  Same kernels, same results.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .dynamics_and_models import _ptr, _wrap, padded_rows, to_device
+
+
+class RolloutGraph(object):
+    """H open-loop steps of `model.rollout_out` for B rows with V vehicles each.
+
+    load(obses, ref_indexes, tape)   copy inputs (host or device) into the static buffers
+    run()                            replay the graph (H launches); results in
+                                     .out5 [H,5,B] (rewards, punish_train, punish_real,
+                                     veh2veh4real, veh2road4real per step) and .final_obs [B,D]
+    """
+
+    def __init__(self, model, B, V, H, use_graph=True):
+        self.model, self.B, self.V, self.H = model, int(B), int(V), int(H)
+        if len(model.veh_mode_list) != V:
+            raise ValueError('the model predicts %d vehicles, rows hold %d' % (len(model.veh_mode_list), V))
+        self.n = int(model.num_future_data)
+        off = model._veh_off
+        self.D = off + 4 * V
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self.obs0 = padded_rows(B, self.D, off, dev)
+        self.buf = [padded_rows(B, self.D, off, dev) for _ in range(2)]
+        self.tape = torch.zeros((H, B, 2), dtype=torch.float32, device=dev)
+        self.out5 = torch.zeros((H, 5, B), dtype=torch.float32, device=dev)
+        self.ref = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.final_obs = _wrap(self.buf[(H - 1) % 2])
+        self._graph = None
+        self.use_graph = use_graph
+        self.launches_per_run = 0
+
+    def load(self, obses, ref_indexes=None, tape=None):
+        self.obs0.copy_(to_device(obses), non_blocking=True)
+        if ref_indexes is not None:
+            self.ref.copy_(to_device(ref_indexes, torch.int32).reshape(-1), non_blocking=True)
+        if tape is not None:
+            self.tape.copy_(to_device(tape), non_blocking=True)
+
+    def _enqueue(self):
+        m, lib = self.model, _lib.load()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        training = m.mode == 'training'
+        path_index = 0 if training else int(m.ref_path.ref_index)
+        ref = _ptr(self.ref) if training else None
+        handle = m.ref_path.handle
+        src = self.obs0
+        ld = self.obs0.stride(0)
+        for t in range(self.H):
+            dst = self.buf[t % 2]
+            _lib.check(lib.ce2e_rollout_step(handle, path_index, ref, _ptr(src), ld, _ptr(self.tape[t]),
+                                             ctypes.byref(m._turn), self.V, self.V, self.n, _ptr(dst), ld,
+                                             _ptr(self.out5[t]), None, self.B, stream))
+            src = dst
+
+    def run(self):
+        if not self.use_graph:
+            self._enqueue()
+            self.launches_per_run = self.H
+            return
+        if self._graph is None:
+            self.model.ref_path.handle            # create the device tables outside the capture
+            n0 = _lib.launch_count()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._enqueue()                   # warm-up launch outside the capture
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            n1 = _lib.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self.launches_per_run = _lib.launch_count() - n1
+            assert self.launches_per_run == n1 - n0 == self.H
+            self._graph = g
+        self._graph.replay()
