@@ -42,7 +42,8 @@ SIGNATURES = {
     'ce2e_paths_destroy': (_i, [_vp]),
     'ce2e_action_transform': (_i, [_vp, _vp, _i64, _vp]),
     'ce2e_dynamics_step': (_i, [_vp, _i64, _vp, _d, _vp, _i64, _vp, _i, _i64, _vp]),
-    'ce2e_find_closest_point': (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp]),
+    'ce2e_find_closest_point': (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _i64, _vp]),
+    'ce2e_grid_build_host': (_i, [_vp, _vp, _c.c_int32, _vp, _vp, _i64]),
     'ce2e_index_points': (_i, [_vp, _i, _vp, _i, _vp, _i64, _vp]),
     'ce2e_tracking_error': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i64, _i64, _vp]),
     'ce2e_compute_rewards': (_i, [_i, _vp, _i64, _vp, _i, _i, _vp, _vp, _i64, _vp]),

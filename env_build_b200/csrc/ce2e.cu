@@ -5,7 +5,7 @@
 //        -Xcompiler -fPIC,-ffp-contract=off -I include -o libce2e.so ce2e.cu
 //
 // Kernel map (reference citations in ce2e_device.cuh / include/ce2e.h):
-//   k_model_step<G>   the fused EnvironmentModel.rollout_out step (also serves
+//   k_model_step      the fused EnvironmentModel.rollout_out step (also serves
 //                     compute_rewards and compute_next_obses through flags)
 //   k_dynamics_step   VehicleDynamics.f_xu / prediction / ego_predict
 //   k_tracking        ReferencePath.tracking_error_vector
@@ -16,6 +16,7 @@
 //   k_ss              EnvironmentModel.ss
 #include "ce2e.h"
 #include "ce2e_device.cuh"
+#include "ce2e_grid.h"
 
 #include <cstdarg>
 #include <cstdio>
@@ -122,6 +123,9 @@ struct ce2e_paths {
     float *full[CE2E_MAX_PATHS];  // device [3, L]: x | y | phi
     float2 *xy10;                 // device [n_paths, stride10]
     float *phi10;                 // device [n_paths, stride10]
+    uint32_t *cells;              // device: candidate grids of all paths, concatenated
+    int cell_off[CE2E_MAX_PATHS];
+    GridSpec grid[CE2E_MAX_PATHS];    // nx == 0: no grid
     int device;
 };
 
@@ -150,8 +154,18 @@ constexpr int F_ACT_NORM = 4;    // actions are normalised: apply the action tra
 constexpr int F_VEC_IN = 8;      // vehicle block of obs_in is 16 B aligned (float4 loads)
 constexpr int F_VEC_OUT = 16;    // same for obs_out
 
+// Candidate grid of find_closest_point as the kernels see it (ce2e_grid.h).
+struct GridView {
+    const uint32_t *cells;   // all paths' cell tables, concatenated
+    int off[4];              // first cell of path p
+    int nx[4], ny[4];        // nx == 0: no grid for this path (always scan everything)
+    float x0[4], y0[4];
+    float inv_h;
+};
+
 struct StepParams {
     PathView pv;
+    GridView gv;
     DynConsts dyn;
     const float *obs_in;
     float *obs_out;
@@ -162,45 +176,74 @@ struct StepParams {
     float *act_scaled_out;
     int64_t ld_in, ld_out, B;
     int task, path_index, V_in, V_out, n_future, flags;
-    int S;                       // lanes cooperating on one row in the ego phase (1, 2, 4, 8)
     ce2e_turn_classes turn;
 };
 
-constexpr int STEP_THREADS = 256;
-constexpr int STEP_WARPS = STEP_THREADS / 32;
+constexpr int STEP_WARPS = 24;           // one 768-thread block per SM
+constexpr int STEP_THREADS = STEP_WARPS * 32;
+constexpr int CV = 4;                    // vehicles per staged chunk (16 B each)
+constexpr int VROW = CV * 4 + 4;         // floats per staged row; +4 makes lane-strided LDS.128 conflict free
+constexpr int QCAP = CV * 4;             // deferred hinge queue entries per lane and chunk
 
-__device__ __forceinline__ float4 load_veh(const float *p, bool vec) {
-    if (vec) return *reinterpret_cast<const float4 *>(p);
-    return make_float4(p[0], p[1], p[2], p[3]);
+struct WarpScratch {
+    float vbuf[2][32 * VROW];            // double-buffered vehicle chunk of the warp's 32 rows
+    float queue[QCAP * 32];              // squared distances that passed the 3.5 m gate, [entry][lane]
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void store_veh(float *p, float4 v, bool vec) {
-    if (vec) {
-        *reinterpret_cast<float4 *>(p) = v;
-    } else {
-        p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// Squared centre distance of one circle pair (DM:225); pairs inside the 3.5 m gate are queued so
+// that the sqrt / hinge arithmetic runs later, densely, in the reference's accumulation order.
+__device__ __forceinline__ void pair_gate(float ex, float ey, float px, float py, float *&qp) {
+    const float dd = sq(ex - px) + sq(ey - py);
+    if (dd < 12.25f) {
+        *qp = dd;
+        qp += 32;
     }
 }
 
-// Work decomposition (DESIGN.md "k_model_step"):
-//   A warp owns a tile of E = 32/S consecutive rows.
-//   Ego phase   : lane -> (row = lane % E, part = lane / E).  Each lane runs the row's scalar
-//                 chain (action scaling, reward terms, road terms, f_xu); the S lanes of a row
-//                 split the waypoint scan and merge with a first-minimum rule.
-//   Vehicle phase: lane -> (row group = lane / G, vehicle = lane % G); the G lanes of a group
-//                 read the row's vehicle block with one coalesced (float4) access per lane,
-//                 add their hinge terms with an xor-shuffle tree and write the predicted
-//                 vehicles back coalesced.
-template <int G>
-__global__ void __launch_bounds__(STEP_THREADS)
+// The nearest-waypoint candidate range of (x, y) on path p: the grid cell's [lo, hi] widened to
+// even bounds, or everything when the point is off the grid / not finite.
+__device__ __forceinline__ void candidate_range(const GridView &gv, int p, int n_even, float x, float y,
+                                                int &k0, int &k1) {
+    k0 = 0;
+    k1 = n_even;
+    const float tx = (x - gv.x0[p]) * gv.inv_h, ty = (y - gv.y0[p]) * gv.inv_h;
+    if (tx >= 0.0f && ty >= 0.0f && tx < (float)gv.nx[p] && ty < (float)gv.ny[p]) {
+        const uint32_t c = __ldg(gv.cells + gv.off[p] + (int)ty * gv.nx[p] + (int)tx);
+        k0 = (int)(c & 0xffffu) & ~1;
+        k1 = ((int)(c >> 16) + 2) & ~1;
+    }
+}
+
+// Work decomposition (DESIGN.md "k_model_step"): one thread per observation row.
+//   A warp owns tiles of 32 consecutive rows (lane = row).
+//   Ego phase    : the row's scalar chain -- action scaling, reward and road terms, f_xu, the
+//                  waypoint scan over the row's candidate range, tracking errors.
+//   Vehicle phase: the warp streams its rows' vehicle blocks through shared memory in chunks of
+//                  CV vehicles with 16 B cp.async copies (coalesced, double buffered); each lane
+//                  walks ITS row's vehicles in the reference's order, updates them in place, and
+//                  the chunk goes back with coalesced 16 B stores.  Circle pairs inside the 3.5 m
+//                  gate are queued per lane and finished (sqrt, hinge^2, sum) densely per chunk.
+__global__ void __launch_bounds__(STEP_THREADS, 1)
 k_model_step(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // shared layout: float4 ego[WARPS][32] | float2 xy[n_paths*stride] | float phi[n_paths*stride]
-    float4 *s_ego = reinterpret_cast<float4 *>(smem_raw);
-    float2 *s_xy = reinterpret_cast<float2 *>(s_ego + STEP_WARPS * 32);
+    // shared layout: WarpScratch[WARPS] | float2 xy[n_paths*stride] | float phi[n_paths*stride]
+    WarpScratch *s_scr = reinterpret_cast<WarpScratch *>(smem_raw);
+    float2 *s_xy = reinterpret_cast<float2 *>(s_scr + STEP_WARPS);
     float *s_phi = reinterpret_cast<float *>(s_xy + (size_t)P.pv.n_paths * P.pv.stride);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool do_next = P.flags & F_NEXT, do_rew = P.flags & F_REWARD;
+    const bool vec_in = P.flags & F_VEC_IN, vec_out = P.flags & F_VEC_OUT;
     if (do_next) {
         const int tot = P.pv.n_paths * P.pv.stride;
         for (int i = tid; i < tot; i += STEP_THREADS) {
@@ -209,25 +252,63 @@ k_model_step(const __grid_constant__ StepParams P) {
         }
         __syncthreads();
     }
-    const int S = P.S, E = 32 / S;
-    const int el = lane % E, part = lane / E;
+    WarpScratch &scr = s_scr[warp];
+    float *const q_base = scr.queue + lane;
+
     const int n_trk = 3 * (P.n_future + 1);
     const int veh_off = 6 + n_trk;
-    constexpr int EPW = 32 / G;              // rows per vehicle-phase pass
-    const int sub = lane / G, vl = lane % G;
-    const int64_t n_tiles = (P.B + E - 1) / E;
-    float4 *my_ego = s_ego + warp * 32;
+    const int64_t n_tiles = (P.B + 31) / 32;
+    const int n_chunks = (P.V_in + CV - 1) / CV;
+    // staging geometry: piece q = lane + 32 i  ->  row (lane / 4) + 8 i, vehicle-in-chunk lane % 4
+    const int p_row = lane >> 2, p_veh = lane & 3;
+    const int p_soff = p_row * VROW + 4 * p_veh;          // float offset inside a chunk buffer
 
-    for (int64_t tile = (int64_t)blockIdx.x * STEP_WARPS + warp; tile < n_tiles;
+    // tile -> (block, warp): consecutive tiles go to different blocks, so every SM gets the same
+    // number of tiles up to one
+    for (int64_t tile = (int64_t)warp * gridDim.x + blockIdx.x; tile < n_tiles;
          tile += (int64_t)gridDim.x * STEP_WARPS) {
-        const int64_t row0 = tile * E;
-        const int64_t row = row0 + el;
+        const int64_t row0 = tile * 32;
+        const int64_t row = row0 + lane;
         const bool valid = row < P.B;
         const int64_t rr = valid ? row : P.B - 1;
         const float *o = P.obs_in + rr * P.ld_in;
+        const int rows_here = (int)min((int64_t)32, P.B - row0);
+        const float *g_in = P.obs_in + (row0 + p_row) * P.ld_in + veh_off + 4 * p_veh;
+        float *g_out = do_next ? P.obs_out + (row0 + p_row) * P.ld_out + veh_off + 4 * p_veh : nullptr;
+
+        auto stage = [&](int ch, float *buf) {
+            const int j = ch * CV + p_veh;
+            if (j < P.V_in) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (p_row + 8 * i < rows_here) {
+                        const float *src = g_in + (int64_t)(8 * i) * P.ld_in + ch * (4 * CV);
+                        float *dst = buf + p_soff + 8 * i * VROW;
+                        if (vec_in) {
+                            cp_async16(dst, src);
+                        } else {
+                            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+                        }
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+        if (n_chunks > 0) stage(0, scr.vbuf[0]);
 
         // ---------------- ego phase ----------------
-        const float vx = o[0], vy = o[1], r = o[2], x = o[3], y = o[4], phi_deg = o[5];
+        float e9[9];
+        if (vec_in && veh_off == 9) {           // o[1] is 16 B aligned: 1 scalar + 2 vector loads
+            e9[0] = o[0];
+            const float4 a = *reinterpret_cast<const float4 *>(o + 1);
+            const float4 b = *reinterpret_cast<const float4 *>(o + 5);
+            e9[1] = a.x; e9[2] = a.y; e9[3] = a.z; e9[4] = a.w;
+            e9[5] = b.x; e9[6] = b.y; e9[7] = b.z; e9[8] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) e9[i] = o[i];
+        }
+        const float vx = e9[0], vy = e9[1], r = e9[2], x = e9[3], y = e9[4], phi_deg = e9[5];
         float steer = P.act[2 * rr], a_x = P.act[2 * rr + 1];
         if (P.flags & F_ACT_NORM) action_transform(steer, a_x, steer, a_x);
         const float phi = deg2rad(phi_deg);
@@ -237,19 +318,19 @@ k_model_step(const __grid_constant__ StepParams P) {
         float rewards = 0.f, v2r_tr = 0.f, v2r_re = 0.f;
         float punish_steer = 0.f, punish_a_x = 0.f, punish_yaw = 0.f, devi_v = 0.f, devi_y = 0.f,
               devi_phi = 0.f;
+        Circles ec = {0.f, 0.f, 0.f, 0.f};
         if (do_rew) {
             punish_steer = -sq(steer);                                   // DM:198-207
             punish_a_x = -sq(a_x);
             punish_yaw = -sq(r);
-            devi_y = -sq(o[6]);
-            devi_phi = -sq(deg2rad(o[7]));
-            devi_v = -sq(o[8]);
+            devi_y = -sq(e9[6]);
+            devi_phi = -sq(deg2rad(e9[7]));
+            devi_v = -sq(e9[8]);
             rewards = ((((0.05f * devi_v + 0.8f * devi_y) + 30.0f * devi_phi) + 0.02f * punish_yaw) +
                        5.0f * punish_steer) + 0.05f * punish_a_x;       // DM:297-298
-            Circles ec = circle_centres(x, y, s, c);
+            ec = circle_centres(x, y, s, c);
             road_terms(P.task, ec.fx, ec.fy, v2r_tr, v2r_re);
             road_terms(P.task, ec.rx, ec.ry, v2r_tr, v2r_re);
-            if (part == 0) my_ego[el] = make_float4(ec.fx, ec.fy, ec.rx, ec.ry);
         }
 
         if (do_next) {
@@ -260,83 +341,103 @@ k_model_step(const __grid_constant__ StepParams P) {
             const bool p_ok = (p >= 0) && (p < P.pv.n_paths);
             p = p_ok ? p : 0;
             const float2 *t_xy = s_xy + (size_t)p * P.pv.stride;
-            // find_closest_point: the S lanes of a row scan disjoint even-aligned chunks
-            const int n_even = (P.pv.N[p] + 1) & ~1;
-            int chunk = ((n_even + S - 1) / S + 1) & ~1;
-            int k0 = min(part * chunk, n_even), k1 = min(k0 + chunk, n_even);
+            int k0, k1;
+            candidate_range(P.gv, p, (P.pv.N[p] + 1) & ~1, nxt[3], nxt[4], k0, k1);
             float best;
             int bi;
             scan_min(t_xy, k0, k1, nxt[3], nxt[4], best, bi);
-            for (int off = E; off < 32; off <<= 1) {
-                float ob = __shfl_xor_sync(0xffffffffu, best, off);
-                int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-            }
-            if (part == 0 && valid) {
+            if (valid) {
                 float *q = P.obs_out + row * P.ld_out;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) q[i] = nxt[i];
+                float t9[3];
                 if (p_ok) {
                     tracking_from_index(t_xy, s_phi + (size_t)p * P.pv.stride, P.pv.L[p],
                                         P.pv.tail[p], P.task, bi, nxt[3], nxt[4], nxt[5], nxt[0],
-                                        P.n_future, q + 6);
+                                        0, t9);
+                    if (P.n_future > 0)
+                        tracking_from_index(t_xy, s_phi + (size_t)p * P.pv.stride, P.pv.L[p],
+                                            P.pv.tail[p], P.task, bi, nxt[3], nxt[4], nxt[5], nxt[0],
+                                            P.n_future, q + 6);
                 } else {
-                    for (int i = 0; i < n_trk; ++i) q[6 + i] = 0.0f;     // DM:342-343
+                    t9[0] = t9[1] = t9[2] = 0.0f;
+                    for (int i = 3; i < n_trk; ++i) q[6 + i] = 0.0f;     // DM:342-343
+                }
+                if (vec_out && veh_off == 9) {
+                    q[0] = nxt[0];
+                    *reinterpret_cast<float4 *>(q + 1) = make_float4(nxt[1], nxt[2], nxt[3], nxt[4]);
+                    *reinterpret_cast<float4 *>(q + 5) = make_float4(nxt[5], t9[0], t9[1], t9[2]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) q[i] = nxt[i];
+                    q[6] = t9[0]; q[7] = t9[1]; q[8] = t9[2];
                 }
             }
         }
-        if (P.act_scaled_out && part == 0 && valid) {
+        if (P.act_scaled_out && valid) {
             P.act_scaled_out[2 * row] = steer;
             P.act_scaled_out[2 * row + 1] = a_x;
         }
-        __syncwarp();
 
         // ---------------- vehicle phase ----------------
         float v2v_tr = 0.f, v2v_re = 0.f;
-        if (P.V_in > 0) {
-            const bool vec_in = P.flags & F_VEC_IN, vec_out = P.flags & F_VEC_OUT;
-            for (int p0 = 0; p0 < E; p0 += EPW) {
-                const int e2 = p0 + sub;
-                const bool ev = (e2 < E) && (row0 + e2 < P.B);
-                float acc_tr = 0.f, acc_re = 0.f;
-                if (ev) {
-                    const float4 ec = do_rew ? my_ego[e2] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float *vin = P.obs_in + (row0 + e2) * P.ld_in + veh_off;
-                    float *vout = do_next ? P.obs_out + (row0 + e2) * P.ld_out + veh_off : nullptr;
-                    for (int j = vl; j < P.V_in; j += G) {
-                        const float4 v = load_veh(vin + 4 * j, vec_in);
-                        const float th = deg2rad(v.w);
-                        float vs, vc;
-                        sincosf(th, &vs, &vc);
-                        if (do_rew) {
-                            const Circles vcirc = circle_centres(v.x, v.y, vs, vc);
-                            pair_term(ec.x, ec.y, vcirc.fx, vcirc.fy, acc_tr, acc_re);
-                            pair_term(ec.x, ec.y, vcirc.rx, vcirc.ry, acc_tr, acc_re);
-                            pair_term(ec.z, ec.w, vcirc.fx, vcirc.fy, acc_tr, acc_re);
-                            pair_term(ec.z, ec.w, vcirc.rx, vcirc.ry, acc_tr, acc_re);
-                        }
-                        if (do_next && j < P.V_out)
-                            store_veh(vout + 4 * j, veh_predict_one(v, th, vs, vc, P.turn.tc[j]),
-                                      vec_out);
-                    }
-                }
-                if (do_rew) {
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            float *buf = scr.vbuf[ch & 1];
+            if (ch + 1 < n_chunks) stage(ch + 1, scr.vbuf[(ch + 1) & 1]);
+            else cp_async_commit();
+            cp_async_wait<1>();
+            __syncwarp();
+            float *qp = q_base;
+            float4 *slot = reinterpret_cast<float4 *>(buf + lane * VROW);
+            const int n_here = min(CV, P.V_in - ch * CV);
 #pragma unroll
-                    for (int off = G / 2; off > 0; off >>= 1) {
-                        acc_tr += __shfl_xor_sync(0xffffffffu, acc_tr, off);
-                        acc_re += __shfl_xor_sync(0xffffffffu, acc_re, off);
+            for (int jj = 0; jj < CV; ++jj) {
+                if (jj < n_here) {
+                    const int j = ch * CV + jj;
+                    const float4 v = slot[jj];
+                    const float th = deg2rad(v.w);
+                    float vs, vc;
+                    sincosf(th, &vs, &vc);
+                    if (do_rew) {
+                        const Circles w = circle_centres(v.x, v.y, vs, vc);
+                        pair_gate(ec.fx, ec.fy, w.fx, w.fy, qp);
+                        pair_gate(ec.fx, ec.fy, w.rx, w.ry, qp);
+                        pair_gate(ec.rx, ec.ry, w.fx, w.fy, qp);
+                        pair_gate(ec.rx, ec.ry, w.rx, w.ry, qp);
                     }
-                    // hand the sums to the lane that owns the row in the ego phase
-                    const int src = ((lane - p0) * G) & 31;
-                    const float g_tr = __shfl_sync(0xffffffffu, acc_tr, src);
-                    const float g_re = __shfl_sync(0xffffffffu, acc_re, src);
-                    if (lane >= p0 && lane < p0 + EPW) { v2v_tr = g_tr; v2v_re = g_re; }
+                    if (do_next && j < P.V_out) slot[jj] = veh_predict_one(v, th, vs, vc, P.turn.tc[j]);
                 }
             }
+            if (do_rew) {
+                const int cnt = (int)(qp - q_base) >> 5;
+                const int n_max = __reduce_max_sync(0xffffffffu, cnt);
+                for (int i = 0; i < n_max; ++i) {
+                    if (i < cnt) {
+                        const float d = __fsqrt_rn(q_base[i * 32]);
+                        const float g35 = d - 3.5f, g25 = d - 2.5f;
+                        v2v_tr = v2v_tr + ((g35 < 0.0f) ? sq(g35) : 0.0f);
+                        v2v_re = v2v_re + ((g25 < 0.0f) ? sq(g25) : 0.0f);
+                    }
+                }
+            }
+            __syncwarp();
+            if (do_next && ch * CV + p_veh < P.V_out) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (p_row + 8 * i < rows_here) {
+                        float *dst = g_out + (int64_t)(8 * i) * P.ld_out + ch * (4 * CV);
+                        const float *src = buf + p_soff + 8 * i * VROW;
+                        if (vec_out) {
+                            *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(src);
+                        } else {
+                            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+                        }
+                    }
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
+        cp_async_wait<0>();
 
-        if (do_rew && part == 0 && valid) {
+        if (do_rew && valid) {
             float *o5 = P.out5;
             o5[row] = rewards;
             o5[P.B + row] = v2v_tr + v2r_tr;                              // DM:299
@@ -356,9 +457,18 @@ k_model_step(const __grid_constant__ StepParams P) {
     }
 }
 
-int pick_group(int V) {
-    int g = 1;
-    while (g < V && g < 32) g <<= 1;
+GridView make_grid_view(const ce2e_paths *p) {
+    GridView g;
+    memset(&g, 0, sizeof(g));
+    g.cells = p->cells;
+    g.inv_h = (float)(1.0 / GRID_H);
+    for (int i = 0; i < p->n_paths; ++i) {
+        g.off[i] = p->cell_off[i];
+        g.nx[i] = p->grid[i].nx;
+        g.ny[i] = p->grid[i].ny;
+        g.x0[i] = p->grid[i].x0;
+        g.y0[i] = p->grid[i].y0;
+    }
     return g;
 }
 
@@ -366,33 +476,19 @@ int launch_model_step(StepParams &P, cudaStream_t st) {
     DeviceInfo *di;
     int rc = device_info(&di);
     if (rc) return rc;
-    // lanes per row in the ego phase: keep >= ~16 warps per SM busy when the batch is small
-    int S = 1;
-    while (S < 8 && (P.B * S + 31) / 32 < (int64_t)di->sms * 16) S <<= 1;
-    if (!(P.flags & F_NEXT)) S = 1;
-    P.S = S;
-    const int E = 32 / S;
-    const int64_t n_tiles = (P.B + E - 1) / E;
-    size_t smem = (size_t)P.pv.n_paths * P.pv.stride * 12 + STEP_WARPS * 32 * sizeof(float4);
+    const int64_t n_tiles = (P.B + 31) / 32;
+    size_t smem = (size_t)P.pv.n_paths * P.pv.stride * 12 + STEP_WARPS * sizeof(WarpScratch);
     if ((int)smem > di->max_smem_optin)
         return fail(CE2E_ERR_SHAPE, "path tables need %zu B of shared memory (max %d)", smem,
                     di->max_smem_optin);
-    const int G = pick_group(P.V_in);
-    void (*kern)(const StepParams) = nullptr;
-    switch (G) {
-        case 1: kern = k_model_step<1>; break;
-        case 2: kern = k_model_step<2>; break;
-        case 4: kern = k_model_step<4>; break;
-        case 8: kern = k_model_step<8>; break;
-        case 16: kern = k_model_step<16>; break;
-        default: kern = k_model_step<32>; break;
+    static thread_local size_t smem_set = 0;
+    if (smem > smem_set) {
+        CE2E_CUDA(cudaFuncSetAttribute(k_model_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
     }
-    if (smem > 48 * 1024)
-        CE2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t blocks = (n_tiles + STEP_WARPS - 1) / STEP_WARPS;
-    const int64_t max_blocks = (int64_t)di->sms * 8;
-    if (blocks > max_blocks) blocks = max_blocks;
-    kern<<<(unsigned)blocks, STEP_THREADS, smem, st>>>(P);
+    // one persistent block per SM; never more blocks than tiles
+    const int64_t blocks = n_tiles < di->sms ? n_tiles : di->sms;
+    k_model_step<<<(unsigned)blocks, STEP_THREADS, smem, st>>>(P);
     return after_launch("k_model_step");
 }
 
@@ -433,11 +529,11 @@ __global__ void k_dynamics_step(const __grid_constant__ DynConsts K, const float
 }
 
 // tracking_error_vector: one thread per row, decimated tables read through the read-only path.
-__global__ void k_tracking(const __grid_constant__ PathView pv, int task, int path_index,
-                           const int32_t *__restrict__ ref_idx, const float *__restrict__ xs,
-                           const float *__restrict__ ys, const float *__restrict__ phis,
-                           const float *__restrict__ vs, int n_future, float *__restrict__ out,
-                           int64_t ld_out, int64_t B) {
+__global__ void k_tracking(const __grid_constant__ PathView pv, const __grid_constant__ GridView gv,
+                           int task, int path_index, const int32_t *__restrict__ ref_idx,
+                           const float *__restrict__ xs, const float *__restrict__ ys,
+                           const float *__restrict__ phis, const float *__restrict__ vs, int n_future,
+                           float *__restrict__ out, int64_t ld_out, int64_t B) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     int p = ref_idx ? ref_idx[i] : path_index;
@@ -448,11 +544,32 @@ __global__ void k_tracking(const __grid_constant__ PathView pv, int task, int pa
     }
     const float x = xs[i], y = ys[i];
     float best;
-    int bi;
+    int bi, k0, k1;
     const float2 *t_xy = pv.xy + (size_t)p * pv.stride;
-    scan_min(t_xy, 0, (pv.N[p] + 1) & ~1, x, y, best, bi);
+    candidate_range(gv, p, (pv.N[p] + 1) & ~1, x, y, k0, k1);
+    scan_min(t_xy, k0, k1, x, y, best, bi);
     tracking_from_index(t_xy, pv.phi + (size_t)p * pv.stride, pv.L[p], pv.tail[p], task, bi, x, y,
                         phis[i], vs[i], n_future, q);
+}
+
+// find_closest_point, ratio 10, through the candidate grid (the path the fused step takes).
+__global__ void k_closest10(const __grid_constant__ PathView pv, const __grid_constant__ GridView gv, int p,
+                            const float *__restrict__ xs, const float *__restrict__ ys,
+                            int64_t *__restrict__ idx_out, float *__restrict__ pts_out, int64_t B) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float x = xs[i], y = ys[i];
+    float best;
+    int bi, k0, k1;
+    const float2 *t_xy = pv.xy + (size_t)p * pv.stride;
+    candidate_range(gv, p, (pv.N[p] + 1) & ~1, x, y, k0, k1);
+    scan_min(t_xy, k0, k1, x, y, best, bi);
+    if (idx_out) idx_out[i] = 10 * (int64_t)bi;
+    if (pts_out) {
+        pts_out[i] = t_xy[bi].x;
+        pts_out[B + i] = t_xy[bi].y;
+        pts_out[2 * B + i] = pv.phi[(size_t)p * pv.stride + bi];
+    }
 }
 
 // find_closest_point with an arbitrary decimation ratio on the full table [3, L].
@@ -601,6 +718,7 @@ int model_step_common(const ce2e_paths *paths, int task, int path_index, const i
             return fail(CE2E_ERR_PATH, "path_index %d outside [0, %d)", path_index, paths->n_paths);
         if (obs_out == obs_in) return fail(CE2E_ERR_SHAPE, "obs_out must not alias obs_in");
         P.pv = make_view(paths);
+        P.gv = make_grid_view(paths);
         if (turn) P.turn = *turn;
     } else {
         P.pv.n_paths = 0;
@@ -672,6 +790,22 @@ int ce2e_paths_create(int task, int n_paths, const int32_t *lens, const float *c
         if (e == cudaSuccess) e = cudaMemcpy(h->full[i] + L, ys[i], sizeof(float) * L, cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(h->full[i] + 2 * (size_t)L, phis[i], sizeof(float) * L, cudaMemcpyHostToDevice);
     }
+    // candidate grids of find_closest_point (ce2e_grid.h), one per path
+    std::vector<uint32_t> all_cells;
+    for (int i = 0; i < n_paths; ++i) {
+        const int n10 = h->N10[i];
+        std::vector<float> wx(n10), wy(n10);
+        for (int k = 0; k < n10; ++k) { wx[k] = xs[i][10 * k]; wy[k] = ys[i][10 * k]; }
+        std::vector<uint32_t> cells;
+        h->cell_off[i] = (int)all_cells.size();
+        if (build_candidate_grid(wx.data(), wy.data(), n10, h->grid[i], cells))
+            all_cells.insert(all_cells.end(), cells.begin(), cells.end());
+        else
+            h->grid[i].nx = h->grid[i].ny = 0;
+    }
+    if (all_cells.empty()) all_cells.push_back(0u);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->cells, sizeof(uint32_t) * all_cells.size());
+    if (e == cudaSuccess) e = cudaMemcpy(h->cells, all_cells.data(), sizeof(uint32_t) * all_cells.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->xy10, sizeof(float2) * xy.size());
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->phi10, sizeof(float) * ph.size());
     if (e == cudaSuccess) e = cudaMemcpy(h->xy10, xy.data(), sizeof(float2) * xy.size(), cudaMemcpyHostToDevice);
@@ -690,6 +824,7 @@ int ce2e_paths_destroy(ce2e_paths *h) {
         if (h->full[i]) cudaFree(h->full[i]);
     if (h->xy10) cudaFree(h->xy10);
     if (h->phi10) cudaFree(h->phi10);
+    if (h->cells) cudaFree(h->cells);
     free(h);
     return CE2E_OK;
 }
@@ -719,8 +854,8 @@ int ce2e_dynamics_step(const float *states, int64_t ld_states, const float *acti
 }
 
 int ce2e_find_closest_point(const ce2e_paths *paths, int path_index, const float *xs,
-                            const float *ys, int ratio, int64_t *idx_out, float *pts_out,
-                            int64_t B, void *stream) {
+                            const float *ys, int ratio, int brute_force, int64_t *idx_out,
+                            float *pts_out, int64_t B, void *stream) {
     int rc;
     if ((rc = check_batch(B))) return rc;
     if (B == 0) return CE2E_OK;
@@ -728,9 +863,28 @@ int ce2e_find_closest_point(const ce2e_paths *paths, int path_index, const float
     if (path_index < 0 || path_index >= paths->n_paths)
         return fail(CE2E_ERR_PATH, "path_index %d outside [0, %d)", path_index, paths->n_paths);
     if (ratio < 1) return fail(CE2E_ERR_SHAPE, "ratio %d < 1", ratio);
+    if (ratio == 10 && !brute_force) {
+        k_closest10<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
+            make_view(paths), make_grid_view(paths), path_index, xs, ys, idx_out, pts_out, B);
+        return after_launch("k_closest10");
+    }
     k_closest<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
         paths->full[path_index], paths->L[path_index], ratio, xs, ys, idx_out, pts_out, B);
     return after_launch("k_closest");
+}
+
+int ce2e_grid_build_host(const float *wx, const float *wy, int32_t n, float *spec5, uint32_t *cells,
+                         int64_t cells_cap) {
+    if (!wx || !wy || !spec5) return fail(CE2E_ERR_NULL, "NULL argument");
+    GridSpec g;
+    std::vector<uint32_t> c;
+    if (!build_candidate_grid(wx, wy, n, g, c)) return fail(CE2E_ERR_SHAPE, "no grid for this table");
+    spec5[0] = g.x0; spec5[1] = g.y0; spec5[2] = g.inv_h; spec5[3] = (float)g.nx; spec5[4] = (float)g.ny;
+    if (cells) {
+        if ((int64_t)c.size() > cells_cap) return fail(CE2E_ERR_SHAPE, "cells buffer too small");
+        memcpy(cells, c.data(), c.size() * sizeof(uint32_t));
+    }
+    return CE2E_OK;
 }
 
 int ce2e_index_points(const ce2e_paths *paths, int path_index, const int64_t *idx, int n_future,
@@ -758,7 +912,8 @@ int ce2e_tracking_error(const ce2e_paths *paths, int path_index, const int32_t *
         return fail(CE2E_ERR_PATH, "path_index %d outside [0, %d)", path_index, paths->n_paths);
     if (n_future < 0 || ld_out < 3 * (n_future + 1)) return fail(CE2E_ERR_SHAPE, "bad n_future / ld_out");
     k_tracking<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
-        make_view(paths), paths->task, path_index, ref_idx, xs, ys, phis, vs, n_future, out, ld_out, B);
+        make_view(paths), make_grid_view(paths), paths->task, path_index, ref_idx, xs, ys, phis, vs, n_future,
+        out, ld_out, B);
     return after_launch("k_tracking");
 }
 

@@ -261,13 +261,14 @@ class ReferencePath(object):
             pass
 
     # -- queries --------------------------------------------------------------------------
-    def find_closest_point(self, xs, ys, ratio=10):
+    def find_closest_point(self, xs, ys, ratio=10, brute_force=False):
         xs, ys = to_device(xs).reshape(-1).contiguous(), to_device(ys).reshape(-1).contiguous()
         B = xs.shape[0]
         idx = torch.empty((B,), dtype=torch.int64, device=xs.device)
         pts = torch.empty((3, B), dtype=torch.float32, device=xs.device)
         _lib.check(_lib.load().ce2e_find_closest_point(self.handle, int(self.ref_index), _ptr(xs), _ptr(ys),
-                                                       int(ratio), _ptr(idx), _ptr(pts), B, _stream()))
+                                                       int(ratio), int(bool(brute_force)), _ptr(idx), _ptr(pts), B,
+                                                       _stream()))
         return _wrap(idx), (_wrap(pts[0]), _wrap(pts[1]), _wrap(pts[2]))
 
     def future_n_data(self, current_indexs, n):

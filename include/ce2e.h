@@ -87,10 +87,20 @@ int ce2e_dynamics_step(const float *states, int64_t ld_states, const float *acti
 /* ReferencePath.find_closest_point(xs, ys, ratio) (DM:702-715) on path `path_index`:
  * idx_out [B] int64 = ratio * first-argmin of the squared distance over every ratio-th
  * waypoint; pts_out [3,B] contiguous = (x, y, phi_deg) of that waypoint (indexs2points,
- * DM:726-733).  Either output may be NULL.                                                */
+ * DM:726-733).  Either output may be NULL.  With ratio == 10 and brute_force == 0 the scan
+ * is restricted to the candidate range of the query's grid cell (same result, see
+ * ce2e_grid_build_host); brute_force != 0 evaluates every candidate like the reference.     */
 int ce2e_find_closest_point(const ce2e_paths *paths, int path_index, const float *xs,
-                            const float *ys, int ratio, int64_t *idx_out, float *pts_out,
-                            int64_t B, void *stream);
+                            const float *ys, int ratio, int brute_force, int64_t *idx_out,
+                            float *pts_out, int64_t B, void *stream);
+
+/* HOST function (no CUDA): the candidate grid libce2e builds for the n every-10th waypoints
+ * (wx, wy) of one path, as used for find_closest_point (DM:702-715).  spec5 = {x0, y0,
+ * cells per metre, nx, ny}; cells[iy*nx + ix] = lo | hi << 16 means: for every query point
+ * in cell ix = (int)((x - x0) * spec5[2]), iy likewise, the brute-force first-argmin lies in
+ * [lo, hi].  cells may be NULL to query the size.                                           */
+int ce2e_grid_build_host(const float *wx, const float *wy, int32_t n, float *spec5, uint32_t *cells,
+                         int64_t cells_cap);
 
 /* ReferencePath.indexs2points (DM:726-733) / future_n_data (DM:717-724).
  * n_future == 0: pts_out [3,B] = points at clamp(idx).  n_future > 0: pts_out

@@ -141,6 +141,33 @@ def test_tracking_random_bit_exact(dm, task):
     assert np.abs(got[(ref < 0) | (ref > 2)]).max() == 0
 
 
+@pytest.mark.parametrize('task', TASKS)
+def test_candidate_grid_equals_brute_force_on_device(dm, task):
+    """4M query points per path: the grid-restricted scan (what the fused step runs) returns the
+    same index as scanning all candidates, bit for bit -- including points on cell edges, on
+    waypoints, on bisectors between waypoints, far off the map, inf and NaN."""
+    rng = np.random.default_rng(77)
+    rp = dm.ReferencePath(task, 0)
+    n = 1 << 20
+    for pi in range(3):
+        rp.set_path(pi)
+        wx, wy = rp.path[0][::10], rp.path[1][::10]
+        k = rng.integers(0, len(wx), n)
+        k1 = np.minimum(k + 1, len(wx) - 1)
+        sets = [np.stack([wx[k] + rng.normal(0, 2.0, n), wy[k] + rng.normal(0, 2.0, n)], 1),
+                np.stack([rng.uniform(-90, 90, n), rng.uniform(-90, 90, n)], 1),
+                np.stack([np.round(rng.uniform(-80, 80, n) * 2) / 2, wy[k] + rng.normal(0, 1.0, n)], 1),
+                np.stack([(wx[k] + wx[k1]) / 2 + rng.normal(0, 1e-6, n), (wy[k] + wy[k1]) / 2], 1)]
+        pts = np.concatenate(sets).astype(np.float32)
+        pts[:8] = [[np.nan, 0], [0, np.nan], [np.inf, 0], [0, -np.inf], [1e30, 1e30], [-1e6, 3], [0, 0], [wx[5], wy[5]]]
+        xs, ys = torch.as_tensor(pts[:, 0], device='cuda'), torch.as_tensor(pts[:, 1], device='cuda')
+        fast, fpts = rp.find_closest_point(xs, ys)
+        slow, spts = rp.find_closest_point(xs, ys, brute_force=True)
+        assert torch.equal(fast, slow)
+        for a, b in zip(fpts, spts):
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+
+
 # ------------------------------------------------------------------------------------------
 # EnvironmentModel pieces
 # ------------------------------------------------------------------------------------------

@@ -140,3 +140,47 @@ def test_div_const_exact():
         subprocess.run(['gcc', '-O2', '-ffp-contract=off', '-o', exe, src, '-lm'], check=True)
         out = subprocess.run([exe, '257'], check=True, capture_output=True, text=True).stdout
     assert 'mismatches=0' in out and 'FAIL' not in out, out
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_candidate_grid_contains_bruteforce_argmin(lib, task):
+    """ce2e_grid.h: for every query point the fp32 brute-force first-argmin (the oracle's
+    find_closest_point, DM:702-715) must lie inside the [lo, hi] range of the point's cell.
+    Points: uniform over the map, concentrated near the paths, and on / next to cell edges."""
+    from oracle import crossroad_oracle as orc
+    paths = dm.build_path_tables(task)[0]
+    rng = np.random.default_rng(123)
+    for pi, p in enumerate(paths):
+        wx, wy = np.ascontiguousarray(p[0][::10]), np.ascontiguousarray(p[1][::10])
+        spec = np.zeros(5, np.float32)
+        assert lib.ce2e_grid_build_host(wx.ctypes.data, wy.ctypes.data, len(wx), spec.ctypes.data, None, 0) == 0
+        x0, y0, inv_h, nx, ny = spec[0], spec[1], spec[2], int(spec[3]), int(spec[4])
+        cells = np.zeros(nx * ny, np.uint32)
+        assert lib.ce2e_grid_build_host(wx.ctypes.data, wy.ctypes.data, len(wx), spec.ctypes.data,
+                                        cells.ctypes.data, cells.size) == 0
+        n = 60000
+        k = rng.integers(0, len(wx), n)
+        near = np.stack([wx[k] + rng.normal(0, 1.5, n), wy[k] + rng.normal(0, 1.5, n)], 1)
+        uni = np.stack([rng.uniform(x0 - 5, x0 + nx / inv_h + 5, n), rng.uniform(y0 - 5, y0 + ny / inv_h + 5, n)], 1)
+        edge = np.stack([x0 + rng.integers(0, nx, n) / inv_h, y0 + rng.uniform(0, ny, n) / inv_h], 1)
+        edge2 = np.stack([wx[k] + rng.normal(0, 1.0, n), y0 + rng.integers(0, ny, n) / inv_h], 1).astype(np.float32)
+        edge2[:, 1] = np.nextafter(edge2[:, 1], np.float32(-1e9))                 # just below a cell edge
+        onpt = np.stack([wx[k], wy[k]], 1)                                       # exactly on waypoints
+        mid = np.stack([(wx[k] + wx[np.minimum(k + 1, len(wx) - 1)]) / 2,
+                        (wy[k] + wy[np.minimum(k + 1, len(wx) - 1)]) / 2], 1)     # bisector points (ties)
+        pts = np.concatenate([near, uni, edge, edge2, onpt, mid]).astype(np.float32)
+        xs, ys = pts[:, 0], pts[:, 1]
+        rp = orc.ReferencePath(task, pi, path_list=paths)
+        want = rp.find_closest_point(xs, ys)[0] // 10
+        # the device's cell computation, in fp32 (candidate_range in ce2e.cu)
+        tx = (xs - np.float32(x0)) * np.float32(inv_h)
+        ty = (ys - np.float32(y0)) * np.float32(inv_h)
+        inside = (tx >= 0) & (ty >= 0) & (tx < np.float32(nx)) & (ty < np.float32(ny))
+        c = cells[(ty[inside].astype(np.int32) * nx + tx[inside].astype(np.int32))]
+        lo, hi = (c & 0xffff).astype(np.int64), (c >> 16).astype(np.int64)
+        w = want[inside]
+        assert inside.mean() > 0.5
+        assert ((lo <= w) & (w <= hi)).all(), (task, pi, int(((lo > w) | (w > hi)).sum()))
+        # near the path the ranges are a handful of waypoints (that is the point of the grid)
+        d2 = ((xs[inside][:20000, None] - wx[None, :]) ** 2 + (ys[inside][:20000, None] - wy[None, :]) ** 2).min(1)
+        assert (hi - lo + 1)[:20000][d2 < 9].max() <= 8
