@@ -179,7 +179,7 @@ struct StepParams {
     ce2e_turn_classes turn;
 };
 
-constexpr int STEP_WARPS = 24;           // one 768-thread block per SM
+constexpr int STEP_WARPS = 16;           // one 512-thread block per SM (<= 128 registers per thread)
 constexpr int STEP_THREADS = STEP_WARPS * 32;
 constexpr int CV = 4;                    // vehicles per staged chunk (16 B each)
 constexpr int VROW = CV * 4 + 4;         // floats per staged row; +4 makes lane-strided LDS.128 conflict free
@@ -190,9 +190,8 @@ struct WarpScratch {
     float queue[QCAP * 32];              // squared distances that passed the 3.5 m gate, [entry][lane]
 };
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -208,6 +207,23 @@ __device__ __forceinline__ void pair_gate(float ex, float ey, float px, float py
         *qp = dd;
         qp += 32;
     }
+}
+
+// One surrounding vehicle of one row: gate its four circle pairs against the ego circles and
+// return its predicted state (DM:218-229, DM:405-427).  Branch free.
+template <bool REW, bool NEXT>
+__device__ __forceinline__ float4 vehicle_step(float4 v, const Circles &ec, int tc, float *&qp) {
+    const float th = deg2rad(v.w);
+    float vs, vc;
+    sincos_cw(th, vs, vc);
+    if (REW) {
+        const Circles w = circle_centres(v.x, v.y, vs, vc);
+        pair_gate(ec.fx, ec.fy, w.fx, w.fy, qp);
+        pair_gate(ec.fx, ec.fy, w.rx, w.ry, qp);
+        pair_gate(ec.rx, ec.ry, w.fx, w.fy, qp);
+        pair_gate(ec.rx, ec.ry, w.rx, w.ry, qp);
+    }
+    return NEXT ? veh_predict_one(v, th, vs, vc, tc) : v;
 }
 
 // The nearest-waypoint candidate range of (x, y) on path p: the grid cell's [lo, hi] widened to
@@ -233,6 +249,7 @@ __device__ __forceinline__ void candidate_range(const GridView &gv, int p, int n
 //                  walks ITS row's vehicles in the reference's order, updates them in place, and
 //                  the chunk goes back with coalesced 16 B stores.  Circle pairs inside the 3.5 m
 //                  gate are queued per lane and finished (sqrt, hinge^2, sum) densely per chunk.
+template <bool REW, bool NEXT>
 __global__ void __launch_bounds__(STEP_THREADS, 1)
 k_model_step(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -242,9 +259,8 @@ k_model_step(const __grid_constant__ StepParams P) {
     float *s_phi = reinterpret_cast<float *>(s_xy + (size_t)P.pv.n_paths * P.pv.stride);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool do_next = P.flags & F_NEXT, do_rew = P.flags & F_REWARD;
     const bool vec_in = P.flags & F_VEC_IN, vec_out = P.flags & F_VEC_OUT;
-    if (do_next) {
+    if (NEXT) {
         const int tot = P.pv.n_paths * P.pv.stride;
         for (int i = tid; i < tot; i += STEP_THREADS) {
             s_xy[i] = P.pv.xy[i];
@@ -259,9 +275,12 @@ k_model_step(const __grid_constant__ StepParams P) {
     const int veh_off = 6 + n_trk;
     const int64_t n_tiles = (P.B + 31) / 32;
     const int n_chunks = (P.V_in + CV - 1) / CV;
-    // staging geometry: piece q = lane + 32 i  ->  row (lane / 4) + 8 i, vehicle-in-chunk lane % 4
+    // staging geometry: piece i of a lane = row (lane / 4) + 8 i of the tile, vehicle lane % 4 of
+    // the chunk: 4 consecutive lanes move one row's 64 B, a warp instruction moves 8 rows
     const int p_row = lane >> 2, p_veh = lane & 3;
     const int p_soff = p_row * VROW + 4 * p_veh;          // float offset inside a chunk buffer
+    const unsigned s_stage = (unsigned)__cvta_generic_to_shared(scr.vbuf[0] + p_soff);
+    const int ld_in = (int)P.ld_in, ld_out = (int)P.ld_out;
 
     // tile -> (block, warp): consecutive tiles go to different blocks, so every SM gets the same
     // number of tiles up to one
@@ -273,28 +292,35 @@ k_model_step(const __grid_constant__ StepParams P) {
         const int64_t rr = valid ? row : P.B - 1;
         const float *o = P.obs_in + rr * P.ld_in;
         const int rows_here = (int)min((int64_t)32, P.B - row0);
-        const float *g_in = P.obs_in + (row0 + p_row) * P.ld_in + veh_off + 4 * p_veh;
-        float *g_out = do_next ? P.obs_out + (row0 + p_row) * P.ld_out + veh_off + 4 * p_veh : nullptr;
+        const float *g_in = P.obs_in + row0 * P.ld_in + (p_row * ld_in + veh_off + 4 * p_veh);
+        float *g_out = NEXT ? P.obs_out + row0 * P.ld_out + (p_row * ld_out + veh_off + 4 * p_veh) : nullptr;
 
-        auto stage = [&](int ch, float *buf) {
+        auto stage = [&](int ch, int b) {
             const int j = ch * CV + p_veh;
-            if (j < P.V_in) {
+            const float *src = g_in + ch * (4 * CV);
+            if (vec_in && rows_here == 32) {
+                if (j < P.V_in) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        cp_async16(s_stage + (unsigned)((b * 32 + 8 * i) * VROW * 4), src + 8 * i * ld_in);
+                }
+            } else if (j < P.V_in) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (p_row + 8 * i < rows_here) {
-                        const float *src = g_in + (int64_t)(8 * i) * P.ld_in + ch * (4 * CV);
-                        float *dst = buf + p_soff + 8 * i * VROW;
+                        const float *s2 = src + 8 * i * ld_in;
+                        float *dst = scr.vbuf[b] + p_soff + 8 * i * VROW;
                         if (vec_in) {
-                            cp_async16(dst, src);
+                            cp_async16((unsigned)__cvta_generic_to_shared(dst), s2);
                         } else {
-                            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+                            dst[0] = s2[0]; dst[1] = s2[1]; dst[2] = s2[2]; dst[3] = s2[3];
                         }
                     }
                 }
             }
             cp_async_commit();
         };
-        if (n_chunks > 0) stage(0, scr.vbuf[0]);
+        if (n_chunks > 0) stage(0, 0);
 
         // ---------------- ego phase ----------------
         float e9[9];
@@ -313,13 +339,13 @@ k_model_step(const __grid_constant__ StepParams P) {
         if (P.flags & F_ACT_NORM) action_transform(steer, a_x, steer, a_x);
         const float phi = deg2rad(phi_deg);
         float s, c;
-        sincosf(phi, &s, &c);
+        sincos_cw(phi, s, c);
 
         float rewards = 0.f, v2r_tr = 0.f, v2r_re = 0.f;
         float punish_steer = 0.f, punish_a_x = 0.f, punish_yaw = 0.f, devi_v = 0.f, devi_y = 0.f,
               devi_phi = 0.f;
         Circles ec = {0.f, 0.f, 0.f, 0.f};
-        if (do_rew) {
+        if (REW) {
             punish_steer = -sq(steer);                                   // DM:198-207
             punish_a_x = -sq(a_x);
             punish_yaw = -sq(r);
@@ -333,7 +359,7 @@ k_model_step(const __grid_constant__ StepParams P) {
             road_terms(P.task, ec.rx, ec.ry, v2r_tr, v2r_re);
         }
 
-        if (do_next) {
+        if (NEXT) {
             float nxt[6];
             f_xu_next(P.dyn, vx, vy, r, x, y, phi, s, c, steer, a_x, nxt);
             nxt[0] = fminf(fmaxf(nxt[0], 0.0f), 35.0f);                  // ego_predict, DM:390
@@ -380,33 +406,34 @@ k_model_step(const __grid_constant__ StepParams P) {
         // ---------------- vehicle phase ----------------
         float v2v_tr = 0.f, v2v_re = 0.f;
         for (int ch = 0; ch < n_chunks; ++ch) {
-            float *buf = scr.vbuf[ch & 1];
-            if (ch + 1 < n_chunks) stage(ch + 1, scr.vbuf[(ch + 1) & 1]);
+            const int b = ch & 1;
+            float *buf = scr.vbuf[b];
+            if (ch + 1 < n_chunks) stage(ch + 1, b ^ 1);
             else cp_async_commit();
             cp_async_wait<1>();
             __syncwarp();
             float *qp = q_base;
             float4 *slot = reinterpret_cast<float4 *>(buf + lane * VROW);
             const int n_here = min(CV, P.V_in - ch * CV);
+            const int j0 = ch * CV;
+            if (n_here == CV && (!NEXT || j0 + CV <= P.V_out)) {
+                // full chunk: four independent vehicles, interleaved by the compiler
+                float4 v[CV];
 #pragma unroll
-            for (int jj = 0; jj < CV; ++jj) {
-                if (jj < n_here) {
-                    const int j = ch * CV + jj;
-                    const float4 v = slot[jj];
-                    const float th = deg2rad(v.w);
-                    float vs, vc;
-                    sincosf(th, &vs, &vc);
-                    if (do_rew) {
-                        const Circles w = circle_centres(v.x, v.y, vs, vc);
-                        pair_gate(ec.fx, ec.fy, w.fx, w.fy, qp);
-                        pair_gate(ec.fx, ec.fy, w.rx, w.ry, qp);
-                        pair_gate(ec.rx, ec.ry, w.fx, w.fy, qp);
-                        pair_gate(ec.rx, ec.ry, w.rx, w.ry, qp);
-                    }
-                    if (do_next && j < P.V_out) slot[jj] = veh_predict_one(v, th, vs, vc, P.turn.tc[j]);
+                for (int jj = 0; jj < CV; ++jj) v[jj] = slot[jj];
+#pragma unroll
+                for (int jj = 0; jj < CV; ++jj) v[jj] = vehicle_step<REW, NEXT>(v[jj], ec, P.turn.tc[j0 + jj], qp);
+                if (NEXT) {
+#pragma unroll
+                    for (int jj = 0; jj < CV; ++jj) slot[jj] = v[jj];
+                }
+            } else {
+                for (int jj = 0; jj < n_here; ++jj) {
+                    const float4 nv = vehicle_step<REW, NEXT>(slot[jj], ec, P.turn.tc[j0 + jj], qp);
+                    if (NEXT && j0 + jj < P.V_out) slot[jj] = nv;
                 }
             }
-            if (do_rew) {
+            if (REW) {
                 const int cnt = (int)(qp - q_base) >> 5;
                 const int n_max = __reduce_max_sync(0xffffffffu, cnt);
                 for (int i = 0; i < n_max; ++i) {
@@ -419,16 +446,25 @@ k_model_step(const __grid_constant__ StepParams P) {
                 }
             }
             __syncwarp();
-            if (do_next && ch * CV + p_veh < P.V_out) {
+            if (NEXT && j0 + p_veh < P.V_out) {
+                float *dst = g_out + ch * (4 * CV);
+                const float *src = buf + p_soff;
+                if (vec_out && rows_here == 32) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (p_row + 8 * i < rows_here) {
-                        float *dst = g_out + (int64_t)(8 * i) * P.ld_out + ch * (4 * CV);
-                        const float *src = buf + p_soff + 8 * i * VROW;
-                        if (vec_out) {
-                            *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(src);
-                        } else {
-                            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<float4 *>(dst + 8 * i * ld_out) =
+                            *reinterpret_cast<const float4 *>(src + 8 * i * VROW);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (p_row + 8 * i < rows_here) {
+                            float *d2 = dst + 8 * i * ld_out;
+                            const float *s2 = src + 8 * i * VROW;
+                            if (vec_out) {
+                                *reinterpret_cast<float4 *>(d2) = *reinterpret_cast<const float4 *>(s2);
+                            } else {
+                                d2[0] = s2[0]; d2[1] = s2[1]; d2[2] = s2[2]; d2[3] = s2[3];
+                            }
                         }
                     }
                 }
@@ -437,7 +473,7 @@ k_model_step(const __grid_constant__ StepParams P) {
         }
         cp_async_wait<0>();
 
-        if (do_rew && valid) {
+        if (REW && valid) {
             float *o5 = P.out5;
             o5[row] = rewards;
             o5[P.B + row] = v2v_tr + v2r_tr;                              // DM:299
@@ -476,19 +512,26 @@ int launch_model_step(StepParams &P, cudaStream_t st) {
     DeviceInfo *di;
     int rc = device_info(&di);
     if (rc) return rc;
+    if (P.ld_in > (1 << 24) || P.ld_out > (1 << 24)) return fail(CE2E_ERR_SHAPE, "row stride too large");
     const int64_t n_tiles = (P.B + 31) / 32;
     size_t smem = (size_t)P.pv.n_paths * P.pv.stride * 12 + STEP_WARPS * sizeof(WarpScratch);
     if ((int)smem > di->max_smem_optin)
         return fail(CE2E_ERR_SHAPE, "path tables need %zu B of shared memory (max %d)", smem,
                     di->max_smem_optin);
-    static thread_local size_t smem_set = 0;
-    if (smem > smem_set) {
-        CE2E_CUDA(cudaFuncSetAttribute(k_model_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    void (*kern)(const StepParams) = nullptr;
+    const bool rew = P.flags & F_REWARD, next = P.flags & F_NEXT;
+    if (rew && next) kern = k_model_step<true, true>;
+    else if (rew) kern = k_model_step<true, false>;
+    else kern = k_model_step<false, true>;
+    static thread_local size_t smem_set[3] = {0, 0, 0};
+    size_t &set = smem_set[rew && next ? 0 : rew ? 1 : 2];
+    if (smem > set) {
+        CE2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        set = smem;
     }
     // one persistent block per SM; never more blocks than tiles
     const int64_t blocks = n_tiles < di->sms ? n_tiles : di->sms;
-    k_model_step<<<(unsigned)blocks, STEP_THREADS, smem, st>>>(P);
+    kern<<<(unsigned)blocks, STEP_THREADS, smem, st>>>(P);
     return after_launch("k_model_step");
 }
 
@@ -514,7 +557,7 @@ __global__ void k_dynamics_step(const __grid_constant__ DynConsts K, const float
     const float steer = act[2 * i], a_x = act[2 * i + 1];
     const float phi = deg2rad(phi_deg);
     float s, c;
-    sincosf(phi, &s, &c);
+    sincos_cw(phi, s, c);
     float out[6];
     f_xu_next(K, vx, vy, r, x, y, phi, s, c, steer, a_x, out);
     if (clip) out[0] = fminf(fmaxf(out[0], 0.0f), 35.0f);
@@ -631,7 +674,7 @@ __global__ void k_veh_predict(const float *__restrict__ vin, int64_t ld_in,
     const float4 v = make_float4(p[0], p[1], p[2], p[3]);
     const float th = deg2rad(v.w);
     float s, c;
-    sincosf(th, &s, &c);
+    sincos_cw(th, s, c);
     const float4 n = veh_predict_one(v, th, s, c, turn.tc[j]);
     float *q = vout + i * ld_out + 4 * j;
     q[0] = n.x; q[1] = n.y; q[2] = n.z; q[3] = n.w;
@@ -645,17 +688,17 @@ __global__ void k_ss(const float *__restrict__ obs, int64_t ld, const float *__r
     if (i >= B) return;
     const float *o = obs + i * ld, *n = nobs + i * ldn;
     float s, c;
-    sincosf(deg2rad(o[5]), &s, &c);
+    sincos_cw(deg2rad(o[5]), s, c);
     const Circles e0 = circle_centres(o[3], o[4], s, c);
-    sincosf(deg2rad(n[5]), &s, &c);
+    sincos_cw(deg2rad(n[5]), s, c);
     const Circles e1 = circle_centres(n[3], n[4], s, c);
     float acc = 0.f;
     for (int j = 0; j < V; ++j) {
         const float *v = o + veh_off + 4 * j, *w = n + veh_off + 4 * j;
         const float ego2veh = __fsqrt_rn(sq(o[3] - v[0]) + sq(o[4] - v[1]));
-        sincosf(deg2rad(v[3]), &s, &c);
+        sincos_cw(deg2rad(v[3]), s, c);
         const Circles v0 = circle_centres(v[0], v[1], s, c);
-        sincosf(deg2rad(w[3]), &s, &c);
+        sincos_cw(deg2rad(w[3]), s, c);
         const Circles v1 = circle_centres(w[0], w[1], s, c);
         const float ex0[2] = {e0.fx, e0.rx}, ey0[2] = {e0.fy, e0.ry}, ex1[2] = {e1.fx, e1.rx},
                     ey1[2] = {e1.fy, e1.ry};
