@@ -179,15 +179,18 @@ struct StepParams {
     ce2e_turn_classes turn;
 };
 
-constexpr int STEP_WARPS = 16;           // one 512-thread block per SM (<= 128 registers per thread)
+constexpr int STEP_WARPS = 14;           // two 448-thread blocks per SM = 28 warps (<= 72 registers)
 constexpr int STEP_THREADS = STEP_WARPS * 32;
-constexpr int CV = 4;                    // vehicles per staged chunk (16 B each)
-constexpr int VROW = CV * 4 + 4;         // floats per staged row; +4 makes lane-strided LDS.128 conflict free
-constexpr int QCAP = CV * 4;             // deferred hinge queue entries per lane and chunk
+constexpr int RPW = 16;                  // rows per warp tile: two lanes per row
+constexpr int CV = 8;                    // vehicles per staged chunk (16 B each); a lane takes four
+constexpr int VPL = CV / 2;              // vehicles per lane and chunk
+constexpr int QCAP = 4 * VPL;            // deferred hinge queue entries per lane and chunk
 
 struct WarpScratch {
-    float vbuf[2][32 * VROW];            // double-buffered vehicle chunk of the warp's 32 rows
-    float queue[QCAP * 32];              // squared distances that passed the 3.5 m gate, [entry][lane]
+    // double-buffered vehicle chunk: lane l owns floats [16 l, 16 l + 16); its vehicle e sits at
+    // float4 index e ^ ((l >> 1) & 3) (swizzle: lane-strided LDS.128 without bank conflicts)
+    float vbuf[2][32 * 4 * VPL];
+    float queue[QCAP * 32];              // [entry][lane]: squared distances inside the 3.5 m gate
 };
 
 __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
@@ -198,30 +201,39 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
 
-// Squared centre distance of one circle pair (DM:225); pairs inside the 3.5 m gate are queued so
-// that the sqrt / hinge arithmetic runs later, densely, in the reference's accumulation order.
-__device__ __forceinline__ void pair_gate(float ex, float ey, float px, float py, float *&qp) {
+// Squared centre distance of one circle pair (DM:225); pairs inside the 3.5 m gate are queued
+// (shared-memory byte address `qa`, 128 B per entry) so that the sqrt / hinge arithmetic runs
+// later, densely, in the reference's accumulation order.
+__device__ __forceinline__ void pair_gate(float ex, float ey, float px, float py, unsigned &qa) {
     const float dd = sq(ex - px) + sq(ey - py);
     if (dd < 12.25f) {
-        *qp = dd;
-        qp += 32;
+        sts_f32(qa, dd);
+        qa += 128;
     }
 }
 
 // One surrounding vehicle of one row: gate its four circle pairs against the ego circles and
 // return its predicted state (DM:218-229, DM:405-427).  Branch free.
 template <bool REW, bool NEXT>
-__device__ __forceinline__ float4 vehicle_step(float4 v, const Circles &ec, int tc, float *&qp) {
+__device__ __forceinline__ float4 vehicle_step(float4 v, const Circles &ec, int tc, unsigned &qa) {
     const float th = deg2rad(v.w);
     float vs, vc;
     sincos_cw(th, vs, vc);
     if (REW) {
         const Circles w = circle_centres(v.x, v.y, vs, vc);
-        pair_gate(ec.fx, ec.fy, w.fx, w.fy, qp);
-        pair_gate(ec.fx, ec.fy, w.rx, w.ry, qp);
-        pair_gate(ec.rx, ec.ry, w.fx, w.fy, qp);
-        pair_gate(ec.rx, ec.ry, w.rx, w.ry, qp);
+        pair_gate(ec.fx, ec.fy, w.fx, w.fy, qa);
+        pair_gate(ec.fx, ec.fy, w.rx, w.ry, qa);
+        pair_gate(ec.rx, ec.ry, w.fx, w.fy, qa);
+        pair_gate(ec.rx, ec.ry, w.rx, w.ry, qa);
     }
     return NEXT ? veh_predict_one(v, th, vs, vc, tc) : v;
 }
@@ -240,17 +252,21 @@ __device__ __forceinline__ void candidate_range(const GridView &gv, int p, int n
     }
 }
 
-// Work decomposition (DESIGN.md "k_model_step"): one thread per observation row.
-//   A warp owns tiles of 32 consecutive rows (lane = row).
-//   Ego phase    : the row's scalar chain -- action scaling, reward and road terms, f_xu, the
-//                  waypoint scan over the row's candidate range, tracking errors.
+// Work decomposition (DESIGN.md "k_model_step"): two lanes per observation row.
+//   A warp owns tiles of RPW = 16 consecutive rows; lane -> (row = lane / 2, half h = lane % 2).
+//   Ego phase    : both lanes of a row run the row's scalar chain -- action scaling, reward and
+//                  road terms, f_xu, the waypoint scan over the row's candidate range, tracking
+//                  errors; lane h = 0 stores.
 //   Vehicle phase: the warp streams its rows' vehicle blocks through shared memory in chunks of
-//                  CV vehicles with 16 B cp.async copies (coalesced, double buffered); each lane
-//                  walks ITS row's vehicles in the reference's order, updates them in place, and
-//                  the chunk goes back with coalesced 16 B stores.  Circle pairs inside the 3.5 m
-//                  gate are queued per lane and finished (sqrt, hinge^2, sum) densely per chunk.
+//                  CV = 8 vehicles with 16 B cp.async copies (8 lanes move one row's 128 B; double
+//                  buffered); lane h takes vehicles 4h .. 4h+3 of the chunk, two at a time,
+//                  updates them in place, and the chunk goes back with coalesced 16 B stores.
+//                  Circle pairs inside the 3.5 m gate are queued per lane; per chunk lane h = 0
+//                  sums the row's (d - 3.5)^2 terms and lane h = 1 the (d - 2.5)^2 terms, both
+//                  walking the row's queued pairs in the reference's order (vehicle, ego circle,
+//                  vehicle circle), so the sums are bit-identical to the sequential loop.
 template <bool REW, bool NEXT>
-__global__ void __launch_bounds__(STEP_THREADS, 1)
+__global__ void __launch_bounds__(STEP_THREADS, 2)
 k_model_step(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // shared layout: WarpScratch[WARPS] | float2 xy[n_paths*stride] | float phi[n_paths*stride]
@@ -269,51 +285,53 @@ k_model_step(const __grid_constant__ StepParams P) {
         __syncthreads();
     }
     WarpScratch &scr = s_scr[warp];
-    float *const q_base = scr.queue + lane;
+    const int lr = lane >> 1, h = lane & 1;
+    const unsigned q_lane = (unsigned)__cvta_generic_to_shared(scr.queue + lane);
+    const unsigned q_row = (unsigned)__cvta_generic_to_shared(scr.queue + (lane & ~1));
+    const float thr = h ? 2.5f : 3.5f;                      // the hinge this lane sums
+    const int swz = lr & 3;                                 // this lane's slot swizzle
 
     const int n_trk = 3 * (P.n_future + 1);
     const int veh_off = 6 + n_trk;
-    const int64_t n_tiles = (P.B + 31) / 32;
+    const int64_t n_tiles = (P.B + RPW - 1) / RPW;
     const int n_chunks = (P.V_in + CV - 1) / CV;
-    // staging geometry: piece i of a lane = row (lane / 4) + 8 i of the tile, vehicle lane % 4 of
-    // the chunk: 4 consecutive lanes move one row's 64 B, a warp instruction moves 8 rows
-    const int p_row = lane >> 2, p_veh = lane & 3;
-    const int p_soff = p_row * VROW + 4 * p_veh;          // float offset inside a chunk buffer
+    // staging geometry: piece i (0..3) of a lane = row (lane / 8) + 4 i of the tile, vehicle
+    // lane % 8 of the chunk; it lands in the slot of lane 2*row + vehicle/4 at (vehicle%4) ^ (row%4)
+    const int p_row = lane >> 3, p_veh = lane & 7;
+    const int p_soff = (2 * p_row + (p_veh >> 2)) * (4 * VPL) + (((p_veh & 3) ^ (p_row & 3)) << 2);
     const unsigned s_stage = (unsigned)__cvta_generic_to_shared(scr.vbuf[0] + p_soff);
+    constexpr int PIECE_STRIDE = 8 * 4 * VPL;               // floats between a lane's pieces (4 rows)
     const int ld_in = (int)P.ld_in, ld_out = (int)P.ld_out;
 
     // tile -> (block, warp): consecutive tiles go to different blocks, so every SM gets the same
     // number of tiles up to one
     for (int64_t tile = (int64_t)warp * gridDim.x + blockIdx.x; tile < n_tiles;
          tile += (int64_t)gridDim.x * STEP_WARPS) {
-        const int64_t row0 = tile * 32;
-        const int64_t row = row0 + lane;
+        const int64_t row0 = tile * RPW;
+        const int64_t row = row0 + lr;
         const bool valid = row < P.B;
         const int64_t rr = valid ? row : P.B - 1;
         const float *o = P.obs_in + rr * P.ld_in;
-        const int rows_here = (int)min((int64_t)32, P.B - row0);
+        const int rows_here = (int)min((int64_t)RPW, P.B - row0);
         const float *g_in = P.obs_in + row0 * P.ld_in + (p_row * ld_in + veh_off + 4 * p_veh);
         float *g_out = NEXT ? P.obs_out + row0 * P.ld_out + (p_row * ld_out + veh_off + 4 * p_veh) : nullptr;
 
         auto stage = [&](int ch, int b) {
-            const int j = ch * CV + p_veh;
             const float *src = g_in + ch * (4 * CV);
-            if (vec_in && rows_here == 32) {
-                if (j < P.V_in) {
+            const unsigned dst = s_stage + (unsigned)(b * 32 * 4 * VPL * 4);
+            if (vec_in && rows_here == RPW && (ch + 1) * CV <= P.V_in) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        cp_async16(s_stage + (unsigned)((b * 32 + 8 * i) * VROW * 4), src + 8 * i * ld_in);
-                }
-            } else if (j < P.V_in) {
+                for (int i = 0; i < 4; ++i) cp_async16(dst + (unsigned)(i * PIECE_STRIDE * 4), src + 4 * i * ld_in);
+            } else if (ch * CV + p_veh < P.V_in) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    if (p_row + 8 * i < rows_here) {
-                        const float *s2 = src + 8 * i * ld_in;
-                        float *dst = scr.vbuf[b] + p_soff + 8 * i * VROW;
+                    if (p_row + 4 * i < rows_here) {
+                        const float *s2 = src + 4 * i * ld_in;
                         if (vec_in) {
-                            cp_async16((unsigned)__cvta_generic_to_shared(dst), s2);
+                            cp_async16(dst + (unsigned)(i * PIECE_STRIDE * 4), s2);
                         } else {
-                            dst[0] = s2[0]; dst[1] = s2[1]; dst[2] = s2[2]; dst[3] = s2[3];
+                            float *d2 = scr.vbuf[b] + p_soff + i * PIECE_STRIDE;
+                            d2[0] = s2[0]; d2[1] = s2[1]; d2[2] = s2[2]; d2[3] = s2[3];
                         }
                     }
                 }
@@ -372,7 +390,7 @@ k_model_step(const __grid_constant__ StepParams P) {
             float best;
             int bi;
             scan_min(t_xy, k0, k1, nxt[3], nxt[4], best, bi);
-            if (valid) {
+            if (valid && h == 0) {
                 float *q = P.obs_out + row * P.ld_out;
                 float t9[3];
                 if (p_ok) {
@@ -398,13 +416,13 @@ k_model_step(const __grid_constant__ StepParams P) {
                 }
             }
         }
-        if (P.act_scaled_out && valid) {
+        if (P.act_scaled_out && valid && h == 0) {
             P.act_scaled_out[2 * row] = steer;
             P.act_scaled_out[2 * row + 1] = a_x;
         }
 
         // ---------------- vehicle phase ----------------
-        float v2v_tr = 0.f, v2v_re = 0.f;
+        float acc = 0.f;                 // h = 0: veh2veh4training, h = 1: veh2veh4real
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int b = ch & 1;
             float *buf = scr.vbuf[b];
@@ -412,54 +430,54 @@ k_model_step(const __grid_constant__ StepParams P) {
             else cp_async_commit();
             cp_async_wait<1>();
             __syncwarp();
-            float *qp = q_base;
-            float4 *slot = reinterpret_cast<float4 *>(buf + lane * VROW);
-            const int n_here = min(CV, P.V_in - ch * CV);
-            const int j0 = ch * CV;
-            if (n_here == CV && (!NEXT || j0 + CV <= P.V_out)) {
-                // full chunk: four independent vehicles, interleaved by the compiler
-                float4 v[CV];
+            unsigned qa = q_lane;
+            float4 *slot = reinterpret_cast<float4 *>(buf + lane * (4 * VPL));
+            const int j0 = ch * CV + VPL * h;               // this lane's first vehicle
+            if (j0 + VPL <= P.V_in && (!NEXT || j0 + VPL <= P.V_out)) {
 #pragma unroll
-                for (int jj = 0; jj < CV; ++jj) v[jj] = slot[jj];
-#pragma unroll
-                for (int jj = 0; jj < CV; ++jj) v[jj] = vehicle_step<REW, NEXT>(v[jj], ec, P.turn.tc[j0 + jj], qp);
-                if (NEXT) {
-#pragma unroll
-                    for (int jj = 0; jj < CV; ++jj) slot[jj] = v[jj];
+                for (int e = 0; e < VPL; e += 2) {          // two independent vehicles at a time
+                    float4 v0 = slot[e ^ swz], v1 = slot[(e + 1) ^ swz];
+                    v0 = vehicle_step<REW, NEXT>(v0, ec, P.turn.tc[j0 + e], qa);
+                    v1 = vehicle_step<REW, NEXT>(v1, ec, P.turn.tc[j0 + e + 1], qa);
+                    if (NEXT) { slot[e ^ swz] = v0; slot[(e + 1) ^ swz] = v1; }
                 }
             } else {
-                for (int jj = 0; jj < n_here; ++jj) {
-                    const float4 nv = vehicle_step<REW, NEXT>(slot[jj], ec, P.turn.tc[j0 + jj], qp);
-                    if (NEXT && j0 + jj < P.V_out) slot[jj] = nv;
+                for (int e = 0; e < VPL; ++e) {
+                    if (j0 + e < P.V_in) {
+                        const float4 nv = vehicle_step<REW, NEXT>(slot[e ^ swz], ec, P.turn.tc[j0 + e], qa);
+                        if (NEXT && j0 + e < P.V_out) slot[e ^ swz] = nv;
+                    }
                 }
             }
             if (REW) {
-                const int cnt = (int)(qp - q_base) >> 5;
-                const int n_max = __reduce_max_sync(0xffffffffu, cnt);
-                for (int i = 0; i < n_max; ++i) {
-                    if (i < cnt) {
-                        const float d = __fsqrt_rn(q_base[i * 32]);
-                        const float g35 = d - 3.5f, g25 = d - 2.5f;
-                        v2v_tr = v2v_tr + ((g35 < 0.0f) ? sq(g35) : 0.0f);
-                        v2v_re = v2v_re + ((g25 < 0.0f) ? sq(g25) : 0.0f);
+                const int cnt = (int)(qa - q_lane) >> 7;
+                const int other = __shfl_xor_sync(0xffffffffu, cnt, 1);
+                const int cnt0 = h ? other : cnt, tot = cnt + other;
+                if (__any_sync(0xffffffffu, tot > 0)) {
+                    __syncwarp();
+                    for (int t = 0; t < tot; ++t) {         // the row's queued pairs, in order
+                        const unsigned a = (t < cnt0) ? q_row + (unsigned)t * 128u
+                                                      : q_row + 4u + (unsigned)(t - cnt0) * 128u;
+                        const float g = __fsqrt_rn(lds_f32(a)) - thr;
+                        acc = acc + ((g < 0.0f) ? sq(g) : 0.0f);
                     }
                 }
             }
             __syncwarp();
-            if (NEXT && j0 + p_veh < P.V_out) {
+            if (NEXT) {
                 float *dst = g_out + ch * (4 * CV);
                 const float *src = buf + p_soff;
-                if (vec_out && rows_here == 32) {
+                if (vec_out && rows_here == RPW && (ch + 1) * CV <= P.V_out) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        *reinterpret_cast<float4 *>(dst + 8 * i * ld_out) =
-                            *reinterpret_cast<const float4 *>(src + 8 * i * VROW);
-                } else {
+                        *reinterpret_cast<float4 *>(dst + 4 * i * ld_out) =
+                            *reinterpret_cast<const float4 *>(src + i * PIECE_STRIDE);
+                } else if (ch * CV + p_veh < P.V_out) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        if (p_row + 8 * i < rows_here) {
-                            float *d2 = dst + 8 * i * ld_out;
-                            const float *s2 = src + 8 * i * VROW;
+                        if (p_row + 4 * i < rows_here) {
+                            float *d2 = dst + 4 * i * ld_out;
+                            const float *s2 = src + i * PIECE_STRIDE;
                             if (vec_out) {
                                 *reinterpret_cast<float4 *>(d2) = *reinterpret_cast<const float4 *>(s2);
                             } else {
@@ -473,14 +491,18 @@ k_model_step(const __grid_constant__ StepParams P) {
         }
         cp_async_wait<0>();
 
-        if (REW && valid) {
-            float *o5 = P.out5;
-            o5[row] = rewards;
-            o5[P.B + row] = v2v_tr + v2r_tr;                              // DM:299
-            o5[2 * P.B + row] = v2v_re + v2r_re;                          // DM:300
-            o5[3 * P.B + row] = v2v_re;
-            o5[4 * P.B + row] = v2r_re;
-            if (P.dict16) {
+        if (REW) {
+            const float oacc = __shfl_xor_sync(0xffffffffu, acc, 1);
+            const float v2v_tr = h ? oacc : acc, v2v_re = h ? acc : oacc;
+            if (valid && h == 0) {
+                float *o5 = P.out5;
+                o5[row] = rewards;
+                o5[P.B + row] = v2v_tr + v2r_tr;                          // DM:299
+                o5[2 * P.B + row] = v2v_re + v2r_re;                      // DM:300
+                o5[3 * P.B + row] = v2v_re;
+                o5[4 * P.B + row] = v2r_re;
+            }
+            if (P.dict16 && valid && h == 1) {
                 float *d = P.dict16 + row;
                 const int64_t B = P.B;
                 d[0] = punish_steer; d[B] = punish_a_x; d[2 * B] = punish_yaw; d[3 * B] = devi_v;
@@ -513,7 +535,7 @@ int launch_model_step(StepParams &P, cudaStream_t st) {
     int rc = device_info(&di);
     if (rc) return rc;
     if (P.ld_in > (1 << 24) || P.ld_out > (1 << 24)) return fail(CE2E_ERR_SHAPE, "row stride too large");
-    const int64_t n_tiles = (P.B + 31) / 32;
+    const int64_t n_tiles = (P.B + RPW - 1) / RPW;
     size_t smem = (size_t)P.pv.n_paths * P.pv.stride * 12 + STEP_WARPS * sizeof(WarpScratch);
     if ((int)smem > di->max_smem_optin)
         return fail(CE2E_ERR_SHAPE, "path tables need %zu B of shared memory (max %d)", smem,
@@ -529,8 +551,8 @@ int launch_model_step(StepParams &P, cudaStream_t st) {
         CE2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         set = smem;
     }
-    // one persistent block per SM; never more blocks than tiles
-    const int64_t blocks = n_tiles < di->sms ? n_tiles : di->sms;
+    // two persistent blocks per SM; never more blocks than tiles
+    const int64_t blocks = n_tiles < 2 * di->sms ? n_tiles : 2 * di->sms;
     kern<<<(unsigned)blocks, STEP_THREADS, smem, st>>>(P);
     return after_launch("k_model_step");
 }
