@@ -44,7 +44,7 @@ def workload_config(B, n_gpus):
             'obs_dim': D, 'horizon': H, 'global_batch': B * n_gpus,
             'parallelism': 'rows sharded over %d GPU(s), no data-path collective' % n_gpus,
             'l2': 'obs ping-pong working set %.0f MB < 126 MB L2 (step-to-step reuse is inherent to the '
-                  'rollout); L2 flushed with a 512 MB memset between timed rollouts' % (3 * B * 560 / 1e6)}
+                  'rollout); L2 flushed with a 512 MB memset between timed rollouts' % (3 * B * 576 / 1e6)}
 
 
 def make_inputs(B, seed):
@@ -292,7 +292,7 @@ def run_ours(args):
         extra = {'batch': Bl, 'value': Bl * H * 5 / (ms_l / 1e3), 'launch_us': us_l,
                  'achieved_gbs': BYTES_PER_ENV_STEP * Bl / (us_l * 1e-6) / 1e9,
                  'frac': BYTES_PER_ENV_STEP * Bl / (us_l * 1e-6) / 1e9 / peak,
-                 'note': 'same kernel, batch whose ping-pong buffers (%.0f MB) exceed L2' % (2 * Bl * 560 / 1e6)}
+                 'note': 'same kernel, batch whose ping-pong buffers (%.0f MB) exceed L2' % (2 * Bl * 576 / 1e6)}
         del rl
 
     cpu = None

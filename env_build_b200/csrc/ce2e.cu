@@ -33,6 +33,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int64_t g_launches = 0;
+bool g_use_pdl = getenv("CE2E_NO_PDL") == nullptr;
 
 int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -182,9 +183,8 @@ struct StepParams {
 constexpr int STEP_WARPS = 14;           // two 448-thread blocks per SM = 28 warps (<= 72 registers)
 constexpr int STEP_THREADS = STEP_WARPS * 32;
 constexpr int RPW = 16;                  // rows per warp tile: two lanes per row
-constexpr int CV = 8;                    // vehicles per staged chunk (16 B each); a lane takes four
-constexpr int VPL = CV / 2;              // vehicles per lane and chunk
-constexpr int QCAP = 4 * VPL;            // deferred hinge queue entries per lane and chunk
+constexpr int VPL = 4;                   // vehicles per lane and staged chunk (16 B each)
+constexpr int QCAP = 24;                 // hinge queue entries per lane; flushed before it can overflow
 
 struct WarpScratch {
     // double-buffered vehicle chunk: lane l owns floats [16 l, 16 l + 16); its vehicle e sits at
@@ -196,10 +196,16 @@ struct WarpScratch {
 __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async8(unsigned smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
@@ -254,17 +260,19 @@ __device__ __forceinline__ void candidate_range(const GridView &gv, int p, int n
 
 // Work decomposition (DESIGN.md "k_model_step"): two lanes per observation row.
 //   A warp owns tiles of RPW = 16 consecutive rows; lane -> (row = lane / 2, half h = lane % 2).
-//   Ego phase    : both lanes of a row run the row's scalar chain -- action scaling, reward and
-//                  road terms, f_xu, the waypoint scan over the row's candidate range, tracking
-//                  errors; lane h = 0 stores.
-//   Vehicle phase: the warp streams its rows' vehicle blocks through shared memory in chunks of
-//                  CV = 8 vehicles with 16 B cp.async copies (8 lanes move one row's 128 B; double
-//                  buffered); lane h takes vehicles 4h .. 4h+3 of the chunk, two at a time,
-//                  updates them in place, and the chunk goes back with coalesced 16 B stores.
-//                  Circle pairs inside the 3.5 m gate are queued per lane; per chunk lane h = 0
-//                  sums the row's (d - 3.5)^2 terms and lane h = 1 the (d - 2.5)^2 terms, both
-//                  walking the row's queued pairs in the reference's order (vehicle, ego circle,
-//                  vehicle circle), so the sums are bit-identical to the sequential loop.
+//   Ego phase    : both lanes load the row's ego columns and action and take sin/cos of the
+//                  heading; then lane h = 0 evaluates the reward and road terms (DM:198-207,
+//                  DM:231-298) while lane h = 1 integrates f_xu, finds the closest waypoint in the
+//                  row's candidate range and writes the next ego + tracking columns (DM:322-353).
+//   Vehicle phase: the vehicle list is split in two halves, lane h owns half h.  The warp streams
+//                  its rows' vehicle blocks through shared memory, four vehicles per lane at a
+//                  time, with 16 B cp.async copies (4 lanes move 64 contiguous bytes; double
+//                  buffered); a lane updates its vehicles in place, two at a time, and the chunk
+//                  goes back with coalesced 16 B stores.  Circle pairs inside the 3.5 m gate are
+//                  queued per lane and finished (sqrt, both hinge^2 terms) in a dense loop at the
+//                  end of the tile, in the reference's order (vehicle, ego circle, vehicle circle).
+//                  veh2veh = (sum over the first half) + (sum over the second half): a fixed
+//                  order, independent of the batch size.
 template <bool REW, bool NEXT>
 __global__ void __launch_bounds__(STEP_THREADS, 2)
 k_model_step(const __grid_constant__ StepParams P) {
@@ -276,29 +284,38 @@ k_model_step(const __grid_constant__ StepParams P) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool vec_in = P.flags & F_VEC_IN, vec_out = P.flags & F_VEC_OUT;
+    bool tables_pending = false;
     if (NEXT) {
-        const int tot = P.pv.n_paths * P.pv.stride;
-        for (int i = tid; i < tot; i += STEP_THREADS) {
-            s_xy[i] = P.pv.xy[i];
-            s_phi[i] = P.pv.phi[i];
-        }
-        __syncthreads();
+        // path tables -> shared memory with 8 B async copies; they are static, so this may run
+        // before the previous launch has finished (programmatic dependent launch) and is only
+        // waited for right before the first waypoint scan
+        const int tot = P.pv.n_paths * P.pv.stride;           // stride is even: tot * 4 B is a multiple of 8
+        const unsigned sx = (unsigned)__cvta_generic_to_shared(s_xy), sp = (unsigned)__cvta_generic_to_shared(s_phi);
+        for (int i = tid; i < tot; i += STEP_THREADS) cp_async8(sx + 8u * i, P.pv.xy + i);
+        for (int i = tid; i < tot / 2; i += STEP_THREADS) cp_async8(sp + 8u * i, P.pv.phi + 2 * i);
+        cp_async_commit();
+        tables_pending = true;
     }
+    // everything below reads what the previous launch of a rollout wrote
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     WarpScratch &scr = s_scr[warp];
     const int lr = lane >> 1, h = lane & 1;
     const unsigned q_lane = (unsigned)__cvta_generic_to_shared(scr.queue + lane);
-    const unsigned q_row = (unsigned)__cvta_generic_to_shared(scr.queue + (lane & ~1));
-    const float thr = h ? 2.5f : 3.5f;                      // the hinge this lane sums
     const int swz = lr & 3;                                 // this lane's slot swizzle
 
     const int n_trk = 3 * (P.n_future + 1);
     const int veh_off = 6 + n_trk;
     const int64_t n_tiles = (P.B + RPW - 1) / RPW;
-    const int n_chunks = (P.V_in + CV - 1) / CV;
+    // vehicle halves: lane h = 0 owns vehicles [0, H), lane h = 1 owns [H, V)
+    const int H = (((P.V_in + 1) >> 1) + VPL - 1) & ~(VPL - 1);
+    const int n_chunks = H / VPL;
     // staging geometry: piece i (0..3) of a lane = row (lane / 8) + 4 i of the tile, vehicle
-    // lane % 8 of the chunk; it lands in the slot of lane 2*row + vehicle/4 at (vehicle%4) ^ (row%4)
-    const int p_row = lane >> 3, p_veh = lane & 7;
-    const int p_soff = (2 * p_row + (p_veh >> 2)) * (4 * VPL) + (((p_veh & 3) ^ (p_row & 3)) << 2);
+    // (lane % 4) of half (lane / 4) % 2 of the chunk; it lands in the slot of lane
+    // 2*row + half at float4 index (vehicle) ^ (row % 4)
+    const int p_row = lane >> 3, p_half = (lane >> 2) & 1, p_e = lane & 3;
+    const int p_veh = p_half * H + p_e;                     // + VPL * chunk
+    const int p_soff = (2 * p_row + p_half) * (4 * VPL) + ((p_e ^ (p_row & 3)) << 2);
     const unsigned s_stage = (unsigned)__cvta_generic_to_shared(scr.vbuf[0] + p_soff);
     constexpr int PIECE_STRIDE = 8 * 4 * VPL;               // floats between a lane's pieces (4 rows)
     const int ld_in = (int)P.ld_in, ld_out = (int)P.ld_out;
@@ -317,12 +334,12 @@ k_model_step(const __grid_constant__ StepParams P) {
         float *g_out = NEXT ? P.obs_out + row0 * P.ld_out + (p_row * ld_out + veh_off + 4 * p_veh) : nullptr;
 
         auto stage = [&](int ch, int b) {
-            const float *src = g_in + ch * (4 * CV);
+            const float *src = g_in + ch * (4 * VPL);
             const unsigned dst = s_stage + (unsigned)(b * 32 * 4 * VPL * 4);
-            if (vec_in && rows_here == RPW && (ch + 1) * CV <= P.V_in) {
+            if (vec_in && rows_here == RPW && H + (ch + 1) * VPL <= P.V_in) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) cp_async16(dst + (unsigned)(i * PIECE_STRIDE * 4), src + 4 * i * ld_in);
-            } else if (ch * CV + p_veh < P.V_in) {
+            } else if (p_veh + ch * VPL < (p_half ? P.V_in : min(H, P.V_in))) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (p_row + 4 * i < rows_here) {
@@ -339,7 +356,6 @@ k_model_step(const __grid_constant__ StepParams P) {
             cp_async_commit();
         };
         if (n_chunks > 0) stage(0, 0);
-
         // ---------------- ego phase ----------------
         float e9[9];
         if (vec_in && veh_off == 9) {           // o[1] is 16 B aligned: 1 scalar + 2 vector loads
@@ -358,26 +374,35 @@ k_model_step(const __grid_constant__ StepParams P) {
         const float phi = deg2rad(phi_deg);
         float s, c;
         sincos_cw(phi, s, c);
-
-        float rewards = 0.f, v2r_tr = 0.f, v2r_re = 0.f;
-        float punish_steer = 0.f, punish_a_x = 0.f, punish_yaw = 0.f, devi_v = 0.f, devi_y = 0.f,
-              devi_phi = 0.f;
-        Circles ec = {0.f, 0.f, 0.f, 0.f};
-        if (REW) {
-            punish_steer = -sq(steer);                                   // DM:198-207
-            punish_a_x = -sq(a_x);
-            punish_yaw = -sq(r);
-            devi_y = -sq(e9[6]);
-            devi_phi = -sq(deg2rad(e9[7]));
-            devi_v = -sq(e9[8]);
-            rewards = ((((0.05f * devi_v + 0.8f * devi_y) + 30.0f * devi_phi) + 0.02f * punish_yaw) +
-                       5.0f * punish_steer) + 0.05f * punish_a_x;       // DM:297-298
-            ec = circle_centres(x, y, s, c);
-            road_terms(P.task, ec.fx, ec.fy, v2r_tr, v2r_re);
-            road_terms(P.task, ec.rx, ec.ry, v2r_tr, v2r_re);
+        const Circles ec = circle_centres(x, y, s, c);
+        if (tables_pending) {                 // first tile of this warp: the path tables must have
+            cp_async_wait<1>();               // landed (the vehicle chunk staged above may still fly)
+            tables_pending = false;
+            named_barrier_sync(1, STEP_THREADS);
         }
 
-        if (NEXT) {
+        float rewards = 0.f, v2r_tr = 0.f, v2r_re = 0.f;
+        if (REW && (h == 0 || !NEXT)) {                                  // reward lane
+            const float punish_steer = -sq(steer);                       // DM:198-207
+            const float punish_a_x = -sq(a_x);
+            const float punish_yaw = -sq(r);
+            const float devi_y = -sq(e9[6]);
+            const float devi_phi = -sq(deg2rad(e9[7]));
+            const float devi_v = -sq(e9[8]);
+            rewards = ((((0.05f * devi_v + 0.8f * devi_y) + 30.0f * devi_phi) + 0.02f * punish_yaw) +
+                       5.0f * punish_steer) + 0.05f * punish_a_x;       // DM:297-298
+            road_terms(P.task, ec.fx, ec.fy, v2r_tr, v2r_re);
+            road_terms(P.task, ec.rx, ec.ry, v2r_tr, v2r_re);
+            if (P.dict16 && valid && h == 0) {
+                float *d = P.dict16 + row;
+                const int64_t B = P.B;
+                d[0] = punish_steer; d[B] = punish_a_x; d[2 * B] = punish_yaw; d[3 * B] = devi_v;
+                d[4 * B] = devi_y; d[5 * B] = devi_phi; d[6 * B] = 5.0f * punish_steer;
+                d[7 * B] = 0.05f * punish_a_x; d[8 * B] = 0.02f * punish_yaw;
+                d[9 * B] = 0.05f * devi_v; d[10 * B] = 0.8f * devi_y; d[11 * B] = 30.0f * devi_phi;
+            }
+        }
+        if (NEXT && (h == 1 || !REW)) {                                  // dynamics lane
             float nxt[6];
             f_xu_next(P.dyn, vx, vy, r, x, y, phi, s, c, steer, a_x, nxt);
             nxt[0] = fminf(fmaxf(nxt[0], 0.0f), 35.0f);                  // ego_predict, DM:390
@@ -390,7 +415,7 @@ k_model_step(const __grid_constant__ StepParams P) {
             float best;
             int bi;
             scan_min(t_xy, k0, k1, nxt[3], nxt[4], best, bi);
-            if (valid && h == 0) {
+            if (valid && h == 1) {
                 float *q = P.obs_out + row * P.ld_out;
                 float t9[3];
                 if (p_ok) {
@@ -414,15 +439,26 @@ k_model_step(const __grid_constant__ StepParams P) {
                     for (int i = 0; i < 6; ++i) q[i] = nxt[i];
                     q[6] = t9[0]; q[7] = t9[1]; q[8] = t9[2];
                 }
+                if (P.act_scaled_out) {
+                    P.act_scaled_out[2 * row] = steer;
+                    P.act_scaled_out[2 * row + 1] = a_x;
+                }
             }
-        }
-        if (P.act_scaled_out && valid && h == 0) {
-            P.act_scaled_out[2 * row] = steer;
-            P.act_scaled_out[2 * row + 1] = a_x;
         }
 
         // ---------------- vehicle phase ----------------
-        float acc = 0.f;                 // h = 0: veh2veh4training, h = 1: veh2veh4real
+        float v2v_tr = 0.f, v2v_re = 0.f;        // this lane's half of the sums
+        unsigned qa = q_lane;
+        auto flush = [&]() {                      // finish this lane's queued pairs, in order
+            const int cnt = (int)(qa - q_lane) >> 7;
+            for (int i = 0; i < cnt; ++i) {
+                const float d = __fsqrt_rn(lds_f32(q_lane + (unsigned)i * 128u));
+                const float g35 = d - 3.5f, g25 = d - 2.5f;
+                v2v_tr = v2v_tr + ((g35 < 0.0f) ? sq(g35) : 0.0f);
+                v2v_re = v2v_re + ((g25 < 0.0f) ? sq(g25) : 0.0f);
+            }
+            qa = q_lane;
+        };
         for (int ch = 0; ch < n_chunks; ++ch) {
             const int b = ch & 1;
             float *buf = scr.vbuf[b];
@@ -430,10 +466,10 @@ k_model_step(const __grid_constant__ StepParams P) {
             else cp_async_commit();
             cp_async_wait<1>();
             __syncwarp();
-            unsigned qa = q_lane;
             float4 *slot = reinterpret_cast<float4 *>(buf + lane * (4 * VPL));
-            const int j0 = ch * CV + VPL * h;               // this lane's first vehicle
-            if (j0 + VPL <= P.V_in && (!NEXT || j0 + VPL <= P.V_out)) {
+            const int j0 = h * H + ch * VPL;                // this lane's first vehicle of the chunk
+            const int j_end = h ? P.V_in : min(H, P.V_in);  // end of this lane's half
+            if (j0 + VPL <= j_end && (!NEXT || j0 + VPL <= P.V_out)) {
 #pragma unroll
                 for (int e = 0; e < VPL; e += 2) {          // two independent vehicles at a time
                     float4 v0 = slot[e ^ swz], v1 = slot[(e + 1) ^ swz];
@@ -443,36 +479,23 @@ k_model_step(const __grid_constant__ StepParams P) {
                 }
             } else {
                 for (int e = 0; e < VPL; ++e) {
-                    if (j0 + e < P.V_in) {
+                    if (j0 + e < j_end) {
                         const float4 nv = vehicle_step<REW, NEXT>(slot[e ^ swz], ec, P.turn.tc[j0 + e], qa);
                         if (NEXT && j0 + e < P.V_out) slot[e ^ swz] = nv;
                     }
                 }
             }
-            if (REW) {
-                const int cnt = (int)(qa - q_lane) >> 7;
-                const int other = __shfl_xor_sync(0xffffffffu, cnt, 1);
-                const int cnt0 = h ? other : cnt, tot = cnt + other;
-                if (__any_sync(0xffffffffu, tot > 0)) {
-                    __syncwarp();
-                    for (int t = 0; t < tot; ++t) {         // the row's queued pairs, in order
-                        const unsigned a = (t < cnt0) ? q_row + (unsigned)t * 128u
-                                                      : q_row + 4u + (unsigned)(t - cnt0) * 128u;
-                        const float g = __fsqrt_rn(lds_f32(a)) - thr;
-                        acc = acc + ((g < 0.0f) ? sq(g) : 0.0f);
-                    }
-                }
-            }
+            if (REW && __any_sync(0xffffffffu, (int)(qa - q_lane) > (QCAP - 4 * VPL) * 128)) flush();
             __syncwarp();
             if (NEXT) {
-                float *dst = g_out + ch * (4 * CV);
+                float *dst = g_out + ch * (4 * VPL);
                 const float *src = buf + p_soff;
-                if (vec_out && rows_here == RPW && (ch + 1) * CV <= P.V_out) {
+                if (vec_out && rows_here == RPW && H + (ch + 1) * VPL <= P.V_out) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         *reinterpret_cast<float4 *>(dst + 4 * i * ld_out) =
                             *reinterpret_cast<const float4 *>(src + i * PIECE_STRIDE);
-                } else if (ch * CV + p_veh < P.V_out) {
+                } else if (p_veh + ch * VPL < (p_half ? P.V_out : min(H, P.V_out))) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         if (p_row + 4 * i < rows_here) {
@@ -492,26 +515,29 @@ k_model_step(const __grid_constant__ StepParams P) {
         cp_async_wait<0>();
 
         if (REW) {
-            const float oacc = __shfl_xor_sync(0xffffffffu, acc, 1);
-            const float v2v_tr = h ? oacc : acc, v2v_re = h ? acc : oacc;
+            flush();
+            // (first half) + (second half); the reward lane (h = 0, or both when !NEXT) writes
+            const float tr_o = __shfl_xor_sync(0xffffffffu, v2v_tr, 1);
+            const float re_o = __shfl_xor_sync(0xffffffffu, v2v_re, 1);
             if (valid && h == 0) {
+                const float tr = v2v_tr + tr_o, re = v2v_re + re_o;
                 float *o5 = P.out5;
                 o5[row] = rewards;
-                o5[P.B + row] = v2v_tr + v2r_tr;                          // DM:299
-                o5[2 * P.B + row] = v2v_re + v2r_re;                      // DM:300
-                o5[3 * P.B + row] = v2v_re;
+                o5[P.B + row] = tr + v2r_tr;                              // DM:299
+                o5[2 * P.B + row] = re + v2r_re;                          // DM:300
+                o5[3 * P.B + row] = re;
                 o5[4 * P.B + row] = v2r_re;
-            }
-            if (P.dict16 && valid && h == 1) {
-                float *d = P.dict16 + row;
-                const int64_t B = P.B;
-                d[0] = punish_steer; d[B] = punish_a_x; d[2 * B] = punish_yaw; d[3 * B] = devi_v;
-                d[4 * B] = devi_y; d[5 * B] = devi_phi; d[6 * B] = 5.0f * punish_steer;
-                d[7 * B] = 0.05f * punish_a_x; d[8 * B] = 0.02f * punish_yaw;
-                d[9 * B] = 0.05f * devi_v; d[10 * B] = 0.8f * devi_y; d[11 * B] = 30.0f * devi_phi;
-                d[12 * B] = v2v_tr; d[13 * B] = v2r_tr; d[14 * B] = v2v_re; d[15 * B] = v2r_re;
+                if (P.dict16) {
+                    float *d = P.dict16 + row;
+                    const int64_t B = P.B;
+                    d[12 * B] = tr; d[13 * B] = v2r_tr; d[14 * B] = re; d[15 * B] = v2r_re;
+                }
             }
         }
+    }
+    if (tables_pending) {                     // a warp without tiles still owes the block its arrival
+        cp_async_wait<0>();
+        named_barrier_sync(1, STEP_THREADS);
     }
 }
 
@@ -553,8 +579,26 @@ int launch_model_step(StepParams &P, cudaStream_t st) {
     }
     // two persistent blocks per SM; never more blocks than tiles
     const int64_t blocks = n_tiles < 2 * di->sms ? n_tiles : 2 * di->sms;
-    kern<<<(unsigned)blocks, STEP_THREADS, smem, st>>>(P);
-    return after_launch("k_model_step");
+    // programmatic dependent launch: the next step's blocks may start (and stage their tables)
+    // while this grid drains; they wait in griddepcontrol.wait before touching observations
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(STEP_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, P);
+    ++g_launches;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CE2E_ERR_CUDA, "k_model_step launch: %s", cudaGetErrorString(e));
+    }
+    return CE2E_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -78,11 +78,12 @@ def _ld(t):
 
 def padded_rows(B, D, veh_off, device=None):
     """An uninitialised [B, D] fp32 view whose rows are padded so that column `veh_off`
-    (the first vehicle) of every row is 16-byte aligned: row stride is a multiple of 4
-    floats and the view starts (-veh_off) % 4 floats into the allocation."""
-    front = (-veh_off) % 4
-    ld = -(-(front + D) // 4) * 4
-    store = torch.empty(max(B, 1) * ld + 4, dtype=torch.float32, device=device or _device())
+    (the first vehicle) of every row is 64-byte aligned (the kernels need 16 B for their vector
+    path; 64 B makes every staged piece whole 32 B DRAM sectors): row stride is a multiple of 16
+    floats and the view starts (-veh_off) % 16 floats into the allocation."""
+    front = (-veh_off) % 16
+    ld = -(-(front + D) // 16) * 16
+    store = torch.empty(max(B, 1) * ld + 16, dtype=torch.float32, device=device or _device())
     return store.as_strided((B, D), (ld, 1), front)
 
 
