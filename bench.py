@@ -129,7 +129,7 @@ def run_reference(args):
                              'note': 'NumPy fp32 restatement of the reference algorithm (oracle/); the TF2 '
                                      'reference cannot be installed offline'},
             'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -318,18 +318,33 @@ def run_ours(args):
                         'path': 'EnvironmentModel.reset + %d x rollout_out from pinned host buffers' % H},
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                              'frac': achieved / peak, 'traffic': ncu_traffic(), 'peak_source': peak_src,
-                             'kernel': 'k_model_step<32>', 'launch_us': launch_us,
+                             'kernel': 'k_model_step<REW=1,NEXT=1>', 'launch_us': launch_us,
                              'bytes_per_launch': BYTES_PER_ENV_STEP * B,
                              'note': 'algorithmic bytes (8*D+32)*B per launch; at this batch the obs ping-pong '
                                      'fits L2, see large_batch for the HBM-bound rate'},
                 'large_batch': extra or None,
                 'cpu_baseline': cpu}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints while the
+    bench runs (NCCL's version banner, warnings) is diverted to stderr."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
