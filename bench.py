@@ -251,8 +251,6 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.perf_counter()
     ms = timed(runner.run, W, K)
-    t1 = time.perf_counter()
-    clocks = sampler.stop(t0, t1) if sampler else None
     launches = runner.launches_per_run * K
     value = world * B * H * K / (ms / 1e3)
     launch_us = 1e3 * ms / launches
@@ -295,6 +293,8 @@ def run_ours(args):
                  'note': 'same kernel, batch whose ping-pong buffers (%.0f MB) exceed L2' % (2 * Bl * 576 / 1e6)}
         del rl
 
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if sampler else None     # sampled over all GPU legs above
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         arm = CpuArm()
