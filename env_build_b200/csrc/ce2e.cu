@@ -154,6 +154,7 @@ constexpr int F_NEXT = 2;        // compute_next_obses -> obs_out
 constexpr int F_ACT_NORM = 4;    // actions are normalised: apply the action transformation
 constexpr int F_VEC_IN = 8;      // vehicle block of obs_in is 16 B aligned (float4 loads)
 constexpr int F_VEC_OUT = 16;    // same for obs_out
+constexpr int F_GYM_EGO = 32;    // CrossroadEnd2end._get_next_ego_state post-ops (E2E:281-282) instead of DM:390
 
 // Candidate grid of find_closest_point as the kernels see it (ce2e_grid.h).
 struct GridView {
@@ -405,7 +406,12 @@ k_model_step(const __grid_constant__ StepParams P) {
         if (NEXT && (h == 1 || !REW)) {                                  // dynamics lane
             float nxt[6];
             f_xu_next(P.dyn, vx, vy, r, x, y, phi, s, c, steer, a_x, nxt);
-            nxt[0] = fminf(fmaxf(nxt[0], 0.0f), 35.0f);                  // ego_predict, DM:390
+            if (P.flags & F_GYM_EGO) {                                   // E2E:281-282
+                nxt[0] = (nxt[0] >= 0.0f) ? nxt[0] : 0.0f;
+                nxt[5] = wrap_heading(nxt[5]);
+            } else {
+                nxt[0] = fminf(fmaxf(nxt[0], 0.0f), 35.0f);              // ego_predict, DM:390
+            }
             int p = P.ref_idx ? P.ref_idx[rr] : P.path_index;
             const bool p_ok = (p >= 0) && (p < P.pv.n_paths);
             p = p_ok ? p : 0;
@@ -783,6 +789,80 @@ __global__ void k_ss(const float *__restrict__ obs, int64_t ld, const float *__r
     out[i] = acc;
 }
 
+// CrossroadEnd2end._judge_done (E2E:200-256) on the observation AFTER a step, one thread per row.
+// Order of the checks as in the reference: collision (Traffic.collision_check, traffic.py:263-295,
+// with every surrounding vehicle taken as L x W = 4.8 x 2.0 like the ego), road constraint on the
+// four body corners (E2E:171-177, EU:73-104), |delta_y| > 15 (E2E:223-225), yaw-rate bound
+// r_bound = miu_r * g / (|v_x| + 1e-8) with miu_r of the step just taken (E2E:167, 231-242),
+// red light (E2E:244-245; v_light is an input), goal box (E2E:247-256).
+// code: 0 not_done_yet, 1 collision, 2 break_road_constrain, 3 deviate_too_much,
+//       4 break_stability, 5 break_red_light, 6 good_done.
+__device__ __forceinline__ bool feasible_point(int task, float px, float py) {
+    const float road = CE2E_LW3;
+    if (px > -CE2E_HALF && px < CE2E_HALF && py > -CE2E_HALF && py < CE2E_HALF) return true;
+    if (task == 0) return (px > 0.f && px < CE2E_LW && py <= -CE2E_HALF) || (py > 0.f && py < road && px < -CE2E_HALF);
+    if (task == 1) return (px > CE2E_LW && px < CE2E_LW2 && py <= -CE2E_HALF) || (px > 0.f && px < road && py >= CE2E_HALF);
+    return (px > CE2E_LW2 && px < road && py <= -CE2E_HALF) || (py > -road && py < 0.f && px > CE2E_HALF);
+}
+
+__global__ void k_env_done(const __grid_constant__ DynConsts K, int task, const float *__restrict__ obs,
+                           int64_t ld, const float *__restrict__ act_scaled, int V, int veh_off,
+                           int v_light, int8_t *__restrict__ done, int64_t B) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float *o = obs + i * ld;
+    const float vx = o[0], r = o[2], x = o[3], y = o[4], phi = o[5], dy = o[6];
+    float s, c;
+    sincos_cw(deg2rad(phi), s, c);
+    int code = 0;
+    // collision: two-circle model, 10 m box gate, threshold ((w + w)/2 + 0.5)^2
+    {
+        const Circles e = circle_centres(x, y, s, c);
+        const float thr = 6.25f;
+        bool hit = false;
+        for (int j = 0; j < V; ++j) {
+            const float *v = o + veh_off + 4 * j;
+            if (fabsf(v[0] - x) < 10.0f && fabsf(v[1] - y) < 10.0f) {
+                float vs, vc;
+                sincos_cw(deg2rad(v[3]), vs, vc);
+                const Circles w = circle_centres(v[0], v[1], vs, vc);
+                hit = hit || (sq(e.fx - w.fx) + sq(e.fy - w.fy) < thr) || (sq(e.fx - w.rx) + sq(e.fy - w.ry) < thr) ||
+                      (sq(e.rx - w.rx) + sq(e.ry - w.ry) < thr) || (sq(e.rx - w.fx) + sq(e.ry - w.fy) < thr);
+            }
+        }
+        if (hit) code = 1;
+    }
+    if (code == 0) {                                     // four corners (+-l/2, +-w/2) in the world frame
+        const float hl = 2.4f, hw = 1.0f;
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float lx = (k & 2) ? -hl : hl, ly = (k & 1) ? -hw : hw;
+            const float px = (lx * c - ly * s) + x, py = (lx * s + ly * c) + y;
+            ok = ok && feasible_point(task, px, py);
+        }
+        if (!ok) code = 2;
+    }
+    if (code == 0 && fabsf(dy) > 15.0f) code = 3;
+    if (code == 0) {
+        const float a_x = act_scaled[2 * i + 1];
+        const float half_ma = (K.m * a_x) / 2.0f;
+        const float F_xr = (a_x < 0.0f) ? half_ma : K.m * a_x;
+        const float miu_r = sqrtf(sq(K.muFzr) - sq(F_xr)) / K.Fzr;      // DM:69
+        const float r_bound = (miu_r * 9.81f) / (fabsf(vx) + 1e-8f);
+        if (!(-r_bound < r && r < r_bound)) code = 4;
+    }
+    if (code == 0 && v_light != 0 && y > -CE2E_HALF && task != 2) code = 5;
+    if (code == 0) {
+        bool goal;
+        if (task == 0) goal = x < -CE2E_HALF - 10.0f && y > 0.f && y < CE2E_LW3;
+        else if (task == 2) goal = x > CE2E_HALF + 10.0f && y > -CE2E_LW3 && y < 0.f;
+        else goal = y > CE2E_HALF + 10.0f && x > 0.f && x < CE2E_LW3;
+        if (goal) code = 6;
+    }
+    done[i] = (int8_t)code;
+}
+
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 int check_task(int task) {
@@ -1051,6 +1131,22 @@ int ce2e_rollout_step(const ce2e_paths *paths, int path_index, const int32_t *re
     return model_step_common(paths, paths->task, path_index, ref_idx, obs_in, ld_in, act_norm, turn,
                              V_in, V_out, n_future, obs_out, ld_out, out5, nullptr, act_scaled_out,
                              B, F_REWARD | F_NEXT | F_ACT_NORM, stream);
+}
+
+int ce2e_env_step(const ce2e_paths *paths, const int32_t *ref_idx, const float *obs_in, int64_t ld_in,
+                  const float *act_norm, const ce2e_turn_classes *turn, int V, int n_future, int v_light,
+                  float *obs_out, int64_t ld_out, float *out5, float *dict16, float *act_scaled_out,
+                  int8_t *done_out, int64_t B, void *stream) {
+    if (!paths) return fail(CE2E_ERR_NULL, "paths handle is NULL");
+    if (B > 0 && (!ref_idx || !act_scaled_out || !done_out)) return fail(CE2E_ERR_NULL, "NULL argument");
+    int rc = model_step_common(paths, paths->task, 0, ref_idx, obs_in, ld_in, act_norm, turn, V, V, n_future,
+                               obs_out, ld_out, out5, dict16, act_scaled_out, B,
+                               F_REWARD | F_NEXT | F_ACT_NORM | F_GYM_EGO, stream);
+    if (rc || B == 0) return rc;
+    k_env_done<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
+        make_dyn_consts(1.0 / 10.0), paths->task, obs_out, ld_out, act_scaled_out, V,
+        6 + 3 * (n_future + 1), v_light, done_out, B);
+    return after_launch("k_env_done");
 }
 
 int ce2e_veh_predict(const float *veh_in, int64_t ld_in, const ce2e_turn_classes *turn, int V,

@@ -1,0 +1,223 @@
+"""Batched, SUMO-free CrossroadEnd2end.
+
+Mirror of the reference's Gym environment (endtoend.py:43-507, E2E below) for the parts that are
+arithmetic: `step` = action scaling (E2E:258-267) -> compute_reward on the current observation
+(E2E:501-507) -> next ego state (E2E:269-283) -> traffic step -> observation (E2E:285-303) ->
+done logic (E2E:200-256).  The reference couples the traffic step to an external SUMO process
+(traffic.py), which is out of scope; here the surrounding vehicles follow the analytic model the
+reference itself uses for prediction (EnvironmentModel.veh_predict, DM:394-427) and keep their
+observation slots, so B environments advance in ONE fused launch plus a small done kernel
+(ce2e_env_step).  Same method names and return conventions as the reference: with num_envs == 1
+`reset()` returns obs [D] and `step(a[2])` returns (obs [D], reward, done, info) as NumPy / Python
+scalars; with num_envs > 1 everything is batched and stays on the device.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import synthetic as syn
+from .dynamics_and_models import (EnvironmentModel, ReferencePath, VehicleDynamics, _ptr, _stream, _wrap,
+                                  padded_rows, to_device, REWARD_DICT_KEYS)
+from .endtoend_env_utils import EXPECTED_V, L, VEH_NUM, VEHICLE_MODE_DICT, VEHICLE_MODE_LIST, W, turn_class
+
+DONE_TYPES = ('not_done_yet', 'collision', 'break_road_constrain', 'deviate_too_much', 'break_stability',
+              'break_red_light', 'good_done')
+# start-index window of _reset_init_state (E2E:473-478)
+_RESET_SPAN = dict(left=900 + 500, straight=1200 + 500, right=420 + 500)
+
+
+class Box(object):
+    """Minimal stand-in for gym.spaces.Box (gym is not a dependency of this package)."""
+
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype
+
+    def sample(self, rng=None):
+        rng = rng or np.random
+        return rng.uniform(self.low, self.high, self.shape).astype(self.dtype)
+
+
+class CrossroadEnd2end(object):
+    def __init__(self,
+                 training_task,  # 'left', 'straight', 'right'
+                 num_future_data=0,
+                 mode='training',
+                 num_envs=1,
+                 veh_num=None,
+                 auto_reset=False,
+                 traffic_init=None,
+                 **kwargs):
+        self.dynamics = VehicleDynamics()
+        self.training_task = training_task
+        self.num_envs = int(num_envs)
+        self.ref_path = ReferencePath(self.training_task, **kwargs)
+        self.num_future_data = num_future_data
+        self.veh_num = VEH_NUM[training_task] if veh_num is None else int(veh_num)
+        self.veh_mode_dict = VEHICLE_MODE_DICT[self.training_task]
+        self.veh_mode_list = syn.tiled_mode_list(VEHICLE_MODE_LIST[training_task], self.veh_num)
+        self.env_model = EnvironmentModel(training_task, num_future_data, veh_mode_list=self.veh_mode_list)
+        self.env_model.ref_path = self.ref_path
+        self.action_number = 2
+        self.exp_v = EXPECTED_V
+        self.ego_l, self.ego_w = L, W
+        self.action_space = Box(low=-1, high=1, shape=(self.action_number,), dtype=np.float32)
+        self.step_length = 100  # ms
+        self.step_time = self.step_length / 1000.0
+        self.ego_info_dim, self.per_tracking_info_dim, self.per_veh_info_dim = 6, 3, 4
+        self.obs_dim = 6 + 3 * (num_future_data + 1) + 4 * self.veh_num
+        self.observation_space = Box(low=-np.inf, high=np.inf, shape=(self.obs_dim,), dtype=np.float32)
+        self.mode = mode
+        self.auto_reset = auto_reset
+        self.traffic_init = traffic_init
+        self.v_light = 0                     # the model traffic has no signal phases: always green
+        self.done_type = 'not_done_yet'
+        self.reward_info = None
+        self.obs = None
+        self.action = None
+        self.ref_indexes = None
+        self._turn = _lib.make_turn_classes([turn_class(m) for m in self.veh_mode_list])
+        self.seed()
+
+    # -- gym plumbing ---------------------------------------------------------------------------
+    def seed(self, seed=None):
+        self.np_random = np.random.default_rng(seed)
+        return [seed]
+
+    def close(self):
+        self.ref_path.close()
+
+    def set_traj(self, trajectory):
+        """set the real trajectory to reconstruct observation (E2E:793-795)"""
+        self.ref_path = trajectory
+        self.env_model.ref_path = trajectory
+
+    def _squeeze(self, t):
+        return t.numpy()[0] if self.num_envs == 1 else t
+
+    # -- reset ------------------------------------------------------------------------------------
+    def _reset_rows(self, n):
+        """Initial observations of n fresh environments (E2E:472-499 for the ego; the traffic comes
+        from `traffic_init(rng, ego_xy, task, V)` -> [n, V, 4] or, by default, from the synthetic
+        distribution of env_build_b200.synthetic since no simulator is available)."""
+        rng, task, paths = self.np_random, self.training_task, self.ref_path.path_list
+        ref = rng.integers(0, len(paths), n).astype(np.int32) if self.num_envs > 1 else \
+            np.full(n, self.ref_path.ref_index, np.int32)
+        idx = (rng.random(n) * _RESET_SPAN[task]).astype(np.int64) + 700
+        obs = np.zeros((n, self.obs_dim), np.float32)
+        for p in range(len(paths)):
+            m = ref == p
+            obs[m, 3], obs[m, 4], obs[m, 5] = paths[p][0][idx[m]], paths[p][1][idx[m]], paths[p][2][idx[m]]
+        obs[:, 0] = (EXPECTED_V * rng.random(n)).astype(np.float32)
+        if self.veh_num:
+            if self.traffic_init is not None:
+                veh = np.asarray(self.traffic_init(rng, obs[:, 3:5], task, self.veh_num), np.float32)
+            else:
+                veh = syn.make_obs(rng, n, task, self.veh_num, paths, ref, 0, edge_frac=0.0, near_frac=0.1)[:, 9:]
+                veh = veh.reshape(n, self.veh_num, 4)
+                # keep the start collision free: push vehicles inside 6 m of the ego away
+                d = np.hypot(veh[:, :, 0] - obs[:, 3:4], veh[:, :, 1] - obs[:, 4:5])
+                veh[:, :, 0] = np.where(d < 6, veh[:, :, 0] + 30, veh[:, :, 0])
+            obs[:, 6 + 3 * (self.num_future_data + 1):] = veh.reshape(n, -1)
+        return obs, ref
+
+    def _fill_tracking(self, obs_dev, ref_dev):
+        trk = self.ref_path.tracking_error_vector(obs_dev[:, 3], obs_dev[:, 4], obs_dev[:, 5], obs_dev[:, 0],
+                                                  self.num_future_data, ref_indexes=ref_dev)
+        obs_dev[:, 6:6 + trk.shape[1]] = trk
+
+    def reset(self, **kwargs):
+        if kwargs:
+            self.ref_path = ReferencePath(self.training_task, **kwargs)      # E2E:100
+            self.env_model.ref_path = self.ref_path
+        elif self.num_envs == 1:                                             # E2E:100 -> DM:591: a fresh random path
+            self.ref_path.set_path(int(self.np_random.integers(len(self.ref_path.path_list))))
+        obs, ref = self._reset_rows(self.num_envs)
+        veh_off = 6 + 3 * (self.num_future_data + 1)
+        buf = padded_rows(self.num_envs, self.obs_dim, veh_off)
+        buf.copy_(to_device(obs))
+        self.ref_indexes = to_device(ref, torch.int32)
+        self._fill_tracking(buf, self.ref_indexes)
+        self.obs = _wrap(buf)
+        self.action = None
+        self.reward_info = None
+        self.done_type = 'not_done_yet'
+        return self._squeeze(self.obs)
+
+    # -- step -------------------------------------------------------------------------------------
+    def step(self, action):
+        B = self.num_envs
+        act = to_device(np.asarray(action, np.float32) if not isinstance(action, torch.Tensor) else action)
+        act = act.reshape(B, 2).contiguous()
+        obs = self.obs
+        veh_off = 6 + 3 * (self.num_future_data + 1)
+        nxt = padded_rows(B, self.obs_dim, veh_off, obs.device)
+        out5 = torch.empty((5, B), dtype=torch.float32, device=obs.device)
+        d16 = torch.empty((16, B), dtype=torch.float32, device=obs.device)
+        scaled = torch.empty((B, 2), dtype=torch.float32, device=obs.device)
+        done = torch.empty((B,), dtype=torch.int8, device=obs.device)
+        _lib.check(_lib.load().ce2e_env_step(self.ref_path.handle, _ptr(self.ref_indexes), _ptr(obs), obs.stride(0),
+                                             _ptr(act), ctypes.byref(self._turn), self.veh_num,
+                                             int(self.num_future_data), int(self.v_light), _ptr(nxt), nxt.stride(0),
+                                             _ptr(out5), _ptr(d16), _ptr(scaled), _ptr(done), B, _stream()))
+        self.action = _wrap(scaled)
+        self.obs = _wrap(nxt)
+        self.done_code = _wrap(done)
+        reward = out5[0]
+        if B == 1:
+            code = int(done.item())
+            self.done_type = DONE_TYPES[code]
+            self.reward_info = {k: float(d16[i, 0]) for i, k in enumerate(REWARD_DICT_KEYS)}
+            self.reward_info.update({'final_rew': float(reward[0])})
+            info = dict(reward_info=self.reward_info, ref_index=int(self.ref_indexes[0]), done_type=self.done_type,
+                        ego_dynamics=self._ego_dynamics_dict())
+            return self.obs.numpy()[0], float(reward[0]), int(code != 0), info
+        info = dict(done_code=self.done_code, ref_index=self.ref_indexes,
+                    reward_info={k: _wrap(d16[i]) for i, k in enumerate(REWARD_DICT_KEYS)})
+        if self.auto_reset:
+            self._reset_done_rows(done)
+        return self.obs, _wrap(reward), _wrap(done != 0), info
+
+    def _reset_done_rows(self, done):
+        rows = torch.nonzero(done != 0).reshape(-1)
+        n = int(rows.numel())
+        if n == 0:
+            return
+        obs, ref = self._reset_rows(n)
+        fresh = to_device(obs)
+        ref_dev = to_device(ref, torch.int32)
+        self._fill_tracking(fresh, ref_dev)
+        self.obs[rows] = fresh
+        self.ref_indexes[rows] = ref_dev
+
+    # -- reference-named numeric helpers (batch-1 callers) ---------------------------------------
+    def _ego_dynamics_dict(self):
+        o = self.obs.numpy()[0]
+        return dict(v_x=o[0], v_y=o[1], r=o[2], x=o[3], y=o[4], phi=o[5], l=self.ego_l, w=self.ego_w)
+
+    def _action_transformation_for_end2end(self, action):  # [-1, 1]
+        a = self.env_model._action_transformation_for_end2end(np.asarray(action, np.float32).reshape(-1, 2))
+        return a.numpy()[0] if np.ndim(action) == 1 else a
+
+    def compute_reward(self, obs, action):
+        """E2E:501-507: `action` is the scaled action; returns (reward, reward_dict) of one row."""
+        res = self.env_model.compute_rewards(np.asarray(obs, np.float32)[np.newaxis, :],
+                                             np.asarray(action, np.float32)[np.newaxis, :])
+        return res[0].numpy()[0], {k: v.numpy()[0] for k, v in res[5].items()}
+
+    def _get_next_ego_state(self, trans_action):
+        """E2E:269-283 for the current (single) environment."""
+        state = self.obs[:, :6] if self.obs.dim() == 2 else self.obs[None, :6]
+        nxt, par = self.dynamics.prediction(state, np.asarray(trans_action, np.float32).reshape(-1, 2), 10)
+        nxt, par = nxt.numpy(), par.numpy()
+        nxt[:, 0] = np.where(nxt[:, 0] >= 0, nxt[:, 0], 0.)
+        from .endtoend_env_utils import deal_with_phi
+        nxt[:, 5] = [deal_with_phi(float(p)) for p in nxt[:, 5]]
+        return (nxt[0], par[0]) if self.num_envs == 1 else (nxt, par)
+
+    def _get_obs(self, exit_='D'):
+        return self._squeeze(self.obs)
+
+    def render(self, mode='human'):
+        raise NotImplementedError('rendering is out of scope (SURVEY.md section 2)')

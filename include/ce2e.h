@@ -133,6 +133,20 @@ int ce2e_compute_next_obses(const ce2e_paths *paths, int path_index, const int32
                             const ce2e_turn_classes *turn, int V_in, int V_out, int n_future,
                             float *obs_out, int64_t ld_out, int64_t B, void *stream);
 
+/* One step of a batch of SUMO-free CrossroadEnd2end environments (E2E:132-144) whose surrounding
+ * traffic follows the analytic model: action scaling (E2E:258-267) -> compute_reward on obs_in
+ * (E2E:501-507 = DM:186-320; out5 / dict16 as in ce2e_compute_rewards) -> _get_next_ego_state
+ * (E2E:269-283: f_xu at 10 Hz, v_x floored at 0, heading wrapped to (-180, 180]) -> vehicles
+ * advanced by veh_predict (DM:394-427, standing in for Traffic.sim_step) -> _get_obs tracking
+ * part on the row's path ref_idx[i] (E2E:285-303) -> _judge_done on the new state (E2E:200-256,
+ * collision test of traffic.py:263-295).  done_out [B] int8: 0 not_done_yet, 1 collision,
+ * 2 break_road_constrain, 3 deviate_too_much, 4 break_stability, 5 break_red_light, 6 good_done.
+ * act_scaled_out [B,2] is required (the stability bound needs the scaled a_x).               */
+int ce2e_env_step(const ce2e_paths *paths, const int32_t *ref_idx, const float *obs_in, int64_t ld_in,
+                  const float *act_norm, const ce2e_turn_classes *turn, int V, int n_future, int v_light,
+                  float *obs_out, int64_t ld_out, float *out5, float *dict16, float *act_scaled_out,
+                  int8_t *done_out, int64_t B, void *stream);
+
 /* EnvironmentModel.veh_predict (DM:394-427): veh_in/veh_out point at the first vehicle
  * column of each row ([B,4V] with ld_in / ld_out).                                        */
 int ce2e_veh_predict(const float *veh_in, int64_t ld_in, const ce2e_turn_classes *turn, int V,

@@ -605,3 +605,104 @@ def judge_feasible(orig_x, orig_y, task):
         before = LANE_WIDTH * 2 < orig_x < LANE_WIDTH * 3 and orig_y <= -half
         after = -LANE_WIDTH * LANE_NUMBER < orig_y < 0 and orig_x > half
     return bool(before or after or in_middle)
+
+
+def rotate_and_shift_coordination(orig_x, orig_y, orig_d, shift_x, shift_y, rotate_d):
+    """endtoend_env_utils.py:120-154 on float64 arrays (angle output omitted)."""
+    rad = rotate_d * np.pi / 180
+    tx = orig_x * np.cos(rad) + orig_y * np.sin(rad)
+    ty = -orig_x * np.sin(rad) + orig_y * np.cos(rad)
+    return tx - shift_x, ty - shift_y
+
+
+DONE_CODES = ('not_done_yet', 'collision', 'break_road_constrain', 'deviate_too_much', 'break_stability',
+              'break_red_light', 'good_done')
+
+
+def gym_env_step(obs, actions_norm, task, ref_indexes, path_list, mode_list, num_future_data=0, v_light=0):
+    """One step of B independent SUMO-free CrossroadEnd2end environments, vectorised restatement of
+    endtoend.py:132-144 with the surrounding traffic advanced by the analytic model (veh_predict,
+    DM:394-427) in place of Traffic.sim_step, and every surrounding vehicle sized like the ego
+    (4.8 x 2.0) in Traffic.collision_check (traffic.py:263-295).
+
+    PARITY UNPINNED for the done logic: the reference's Gym class needs SUMO and cannot run here,
+    so this part is a restatement only (scalar Python in the reference -> float64 NumPy here).
+
+    Returns (next_obs [B,D] f32, reward [B] f32, done_code [B] int8, margin [B] f64) where margin
+    is the smallest slack of any threshold comparison that decided the row's code."""
+    obs = np.asarray(obs, dtype=f32)
+    B = obs.shape[0]
+    ntr = 3 * (num_future_data + 1)
+    scaled = action_transformation(actions_norm)                                    # E2E:258-267
+    reward = compute_rewards(obs, scaled, task, num_future_data)[0]                 # E2E:501-507
+    nxt, params = f_xu(obs[:, :6], scaled, 1 / 10)                                  # E2E:279
+    nxt = nxt.copy()
+    nxt[:, 0] = np.where(nxt[:, 0] >= 0, nxt[:, 0], f32(0))                         # E2E:281
+    nxt[:, 5] = np.array([deal_with_phi(float(p)) for p in nxt[:, 5]], dtype=f32)   # E2E:282
+    veh = veh_predict(obs[:, 6 + ntr:], mode_list)                                  # stands in for sim_step
+    trk = np.zeros((B, ntr), dtype=f32)
+    ref_indexes = np.asarray(ref_indexes)
+    for pi in range(len(path_list)):                                                # E2E:293-297
+        m = ref_indexes == pi
+        if m.any():
+            rp = ReferencePath(task, pi, path_list=path_list)
+            trk[m] = rp.tracking_error_vector(nxt[m, 3], nxt[m, 4], nxt[m, 5], nxt[m, 0], num_future_data)
+    next_obs = np.concatenate([nxt, trk, veh], 1).astype(f32)
+
+    # ---- _judge_done (E2E:200-256), float64 like the reference's Python scalars ----
+    vx, r, x, y, phi = (nxt[:, i].astype(np.float64) for i in (0, 2, 3, 4, 5))
+    code = np.zeros(B, np.int8)
+    margin = np.full(B, np.inf)
+
+    def decide(cond, slack, c):
+        nonlocal code, margin
+        open_ = code == 0
+        margin = np.where(open_, np.minimum(margin, slack), margin)
+        code = np.where(open_ & cond, np.int8(c), code)
+
+    # collision_check (traffic.py:263-295)
+    lw = (L - W) / 2
+    ex0, ey0 = x + np.cos(phi / 180 * np.pi) * lw, y + np.sin(phi / 180 * np.pi) * lw
+    ex1, ey1 = x - np.cos(phi / 180 * np.pi) * lw, y - np.sin(phi / 180 * np.pi) * lw
+    hit = np.zeros(B, bool)
+    slack = np.full(B, np.inf)
+    thr = ((W + W) / 2 + 0.5) ** 2
+    V = veh.shape[1] // 4
+    for j in range(V):
+        vxx, vyy, vph = (veh[:, 4 * j + k].astype(np.float64) for k in (0, 1, 3))
+        gate = (np.abs(vxx - x) < 10) & (np.abs(vyy - y) < 10)
+        slack = np.minimum(slack, np.minimum(np.abs(np.abs(vxx - x) - 10), np.abs(np.abs(vyy - y) - 10)))
+        sx0, sy0 = vxx + np.cos(vph / 180 * np.pi) * lw, vyy + np.sin(vph / 180 * np.pi) * lw
+        sx1, sy1 = vxx - np.cos(vph / 180 * np.pi) * lw, vyy - np.sin(vph / 180 * np.pi) * lw
+        for (ax, ay, bx, by) in ((ex0, ey0, sx0, sy0), (ex0, ey0, sx1, sy1), (ex1, ey1, sx1, sy1), (ex1, ey1, sx0, sy0)):
+            d2 = (ax - bx) ** 2 + (ay - by) ** 2
+            hit |= gate & (d2 < thr)
+            slack = np.minimum(slack, np.where(gate, np.abs(d2 - thr), np.inf))
+    decide(hit, slack, 1)
+    # _break_road_constrain: four corners (E2E:171-177) through judge_feasible (EU:73-104)
+    ok = np.ones(B, bool)
+    slack = np.full(B, np.inf)
+    for lx, ly in ((L / 2, W / 2), (L / 2, -W / 2), (-L / 2, W / 2), (-L / 2, -W / 2)):
+        px, py = rotate_and_shift_coordination(lx, ly, 0, -x, -y, -phi)
+        ok &= np.array([judge_feasible(a, b, task) for a, b in zip(px, py)], bool)
+        for edge in (-25., 25., 0., LANE_WIDTH, 2 * LANE_WIDTH, 3 * LANE_WIDTH, -3 * LANE_WIDTH):
+            slack = np.minimum(slack, np.minimum(np.abs(px - edge), np.abs(py - edge)))
+    decide(~ok, slack, 2)
+    dy = next_obs[:, 6].astype(np.float64)
+    decide(np.abs(dy) > 15, np.abs(np.abs(dy) - 15), 3)                              # E2E:223-225
+    miu_r = params[:, 3].astype(np.float64)
+    r_bound = miu_r * VEHICLE_PARAMS['g'] / (np.abs(vx) + 1e-8)                      # E2E:167
+    decide(~((-r_bound < r) & (r < r_bound)), np.abs(np.abs(r) - r_bound), 4)       # E2E:231-242
+    decide((v_light != 0) & (y > -CROSSROAD_SIZE / 2) & (task != 'right'), np.abs(y + CROSSROAD_SIZE / 2), 5)
+    road = LANE_NUMBER * LANE_WIDTH
+    if task == 'left':                                                              # E2E:247-256
+        goal = (x < -CROSSROAD_SIZE / 2 - 10) & (0 < y) & (y < road)
+        slack = np.minimum(np.abs(x + 35), np.minimum(np.abs(y), np.abs(y - road)))
+    elif task == 'right':
+        goal = (x > CROSSROAD_SIZE / 2 + 10) & (-road < y) & (y < 0)
+        slack = np.minimum(np.abs(x - 35), np.minimum(np.abs(y), np.abs(y + road)))
+    else:
+        goal = (y > CROSSROAD_SIZE / 2 + 10) & (0 < x) & (x < road)
+        slack = np.minimum(np.abs(y - 35), np.minimum(np.abs(x), np.abs(x - road)))
+    decide(goal, slack, 6)
+    return next_obs, reward, code, margin

@@ -1,0 +1,137 @@
+"""Batched SUMO-free CrossroadEnd2end (env_build_b200/endtoend.py -> ce2e_env_step) against the
+oracle's restatement of endtoend.py:132-256 / traffic.py:263-295.  Needs a GPU.
+Done codes are integers: they must match exactly on every row whose deciding comparison has a
+slack above 1e-3 (the oracle evaluates the predicates in float64 like the reference's Python
+scalars, the kernel in fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TASKS
+from oracle import crossroad_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def e2e():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from env_build_b200 import _lib
+    if _lib.needs_build():
+        _lib.build()
+    from env_build_b200 import endtoend
+    return endtoend
+
+
+def craft(obs, task, paths):
+    """Rows that exercise the done types (collisions come from the synthetic near vehicles)."""
+    o = obs.copy()
+    q = len(o) // 8
+    o[q:6 * q, 9::4] = 400.0                                    # no vehicles around these rows
+    o[2 * q:3 * q, 2] = 3.0                                     # large yaw rate -> break_stability
+    o[2 * q:3 * q, 0] = 9.0
+    goal = dict(left=(-36.0, 5.6, 180.0), straight=(5.6, 36.0, 90.0), right=(36.0, -5.6, 0.0))[task]
+    o[3 * q:4 * q, 3], o[3 * q:4 * q, 4], o[3 * q:4 * q, 5] = goal   # beyond the goal line -> good_done
+    o[3 * q:4 * q, 1:3] = 0
+    off = dict(left=(20.0, -40.0, 90.0), straight=(-10.0, -40.0, 90.0), right=(-3.0, -40.0, 90.0))[task]
+    o[4 * q:5 * q, 3], o[4 * q:5 * q, 4], o[4 * q:5 * q, 5] = off    # off the approach lanes -> road constraint
+    o[5 * q:6 * q, 3] += 25.0                                   # far from the path -> road / deviate
+    return o
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_env_step_matches_oracle(e2e, task):
+    from env_build_b200 import synthetic as syn
+    rng = np.random.default_rng(20210314)
+    B, V = 4000, orc.VEH_NUM[task]
+    env = e2e.CrossroadEnd2end(task, num_envs=B)
+    env.seed(3)
+    env.reset()
+    paths = env.ref_path.path_list
+    ref = syn.make_ref_indexes(rng, B)
+    obs = craft(syn.make_obs(rng, B, task, V, paths, ref), task, paths)
+    act = syn.make_actions(rng, 1, B)[0]
+    env.obs = env.env_model._adopt(obs)
+    env.ref_indexes = torch.as_tensor(ref, device='cuda')
+    got_obs, got_rew, got_done, info = env.step(act)
+    want_obs, want_rew, want_code, margin = orc.gym_env_step(obs, act, task, ref, paths, orc.VEHICLE_MODE_LIST[task])
+    g = got_obs.numpy()
+    assert np.allclose(g[:, :6], want_obs[:, :6], rtol=1e-5, atol=1e-5)
+    assert np.allclose(g[:, 9:], want_obs[:, 9:], rtol=1e-5, atol=1e-5)
+    assert np.allclose(got_rew.numpy(), want_rew, rtol=1e-5, atol=1e-5)
+    # heading wrapped to (-180, 180], v_x floored at 0 (E2E:281-282)
+    assert g[:, 5].max() <= 180.0 and g[:, 5].min() > -180.0 and g[:, 0].min() >= 0.0
+    code = info['done_code'].numpy()
+    ok = margin > 1e-3
+    assert ok.mean() > 0.97
+    assert (code[ok] == want_code[ok]).all(), np.flatnonzero(code[ok] != want_code[ok])[:10]
+    assert (got_done.numpy() == (code != 0)).all()
+    seen = set(np.unique(want_code[ok]).tolist())
+    assert {0, 1, 2, 4, 6} <= seen, seen                       # every branch but red light / deviate exercised here
+
+
+def test_deviate_and_red_light(e2e):
+    """|delta_y| > 15 (E2E:223-225) and the red-light rule (E2E:244-245) need dedicated rows."""
+    from env_build_b200 import synthetic as syn
+    rng = np.random.default_rng(5)
+    task, B, V = 'straight', 512, 9
+    env = e2e.CrossroadEnd2end(task, num_envs=B)
+    env.reset()
+    paths = env.ref_path.path_list
+    ref = np.zeros(B, np.int32)
+    obs = syn.make_obs(rng, B, task, V, paths, ref, edge_frac=0.0)
+    obs[:, 9::4] = 400.0
+    obs[:, 3] = paths[0][0][2000] + rng.uniform(-1, 1, B)
+    obs[:B // 2, 3] -= 20.0                                          # inside the box, 20 m left of the path
+    obs[:, 4] = rng.uniform(-20, 20, B)
+    obs[:, 5] = 90.0
+    obs[:, 1:3] = 0.0
+    act = np.zeros((B, 2), np.float32)
+    for v_light in (0, 1):
+        env.obs = env.env_model._adopt(obs)
+        env.ref_indexes = torch.as_tensor(ref, device='cuda')
+        env.v_light = v_light
+        _, _, _, info = env.step(act)
+        _, _, want, margin = orc.gym_env_step(obs, act, task, ref, paths, orc.VEHICLE_MODE_LIST[task], v_light=v_light)
+        ok = margin > 1e-3
+        assert (info['done_code'].numpy()[ok] == want[ok]).all()
+        assert (want[ok] == 3).any() and ((want[ok] == 5).any() == bool(v_light))
+
+
+def test_single_env_gym_api(e2e):
+    env = e2e.CrossroadEnd2end('left')
+    env.seed(0)
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (41,) and obs.dtype == np.float32
+    assert env.observation_space.shape == (41,) and env.action_space.shape == (2,)
+    total, steps, done = 0.0, 0, 0
+    while not done and steps < 200:                              # README: 200-step episode cap
+        a = np.array([0.0, 0.3], np.float32)
+        prev = obs
+        obs, reward, done, info = env.step(a)
+        r2, rd = env.compute_reward(prev, env._action_transformation_for_end2end(a))
+        assert abs(r2 - reward) <= 1e-5 + 1e-5 * abs(reward)
+        assert set(rd) == set(info['reward_info']) - {'final_rew'}
+        assert isinstance(reward, float) and done in (0, 1) and info['done_type'] in e2e.DONE_TYPES
+        total += reward
+        steps += 1
+    assert steps >= 1 and np.isfinite(total)
+    nxt, par = env._get_next_ego_state(np.array([0.0, 0.0], np.float32))
+    assert nxt.shape == (6,) and par.shape == (4,)
+
+
+def test_auto_reset(e2e):
+    env = e2e.CrossroadEnd2end('right', num_envs=2048, auto_reset=True)
+    env.seed(1)
+    env.reset()
+    rng = np.random.default_rng(0)
+    n_done = 0
+    for _ in range(30):
+        obs, rew, done, info = env.step(rng.uniform(-1, 1, (2048, 2)).astype(np.float32))
+        n_done += int(done.sum())
+        o = obs.numpy()
+        assert np.isfinite(o).all()
+        # rows that were reset start on their path again: tracking error is that of a fresh pose
+        assert np.abs(o[done.numpy(), 6]).max(initial=0.0) < 1.0
+    assert n_done > 0
