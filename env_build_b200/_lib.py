@@ -51,6 +51,7 @@ SIGNATURES = {
                                      _vp, _i64, _i64, _vp]),
     'ce2e_env_step': (_i, [_vp, _vp, _vp, _i64, _vp, _c.POINTER(TurnClasses), _i, _i, _i, _vp, _i64, _vp, _vp, _vp,
                            _vp, _i64, _vp]),
+    'ce2e_judge_done': (_i, [_i, _vp, _i64, _vp, _i, _i, _i, _vp, _i64, _vp]),
     'ce2e_veh_predict': (_i, [_vp, _i64, _c.POINTER(TurnClasses), _i, _vp, _i64, _i64, _vp]),
     'ce2e_rollout_step': (_i, [_vp, _i, _vp, _vp, _i64, _vp, _c.POINTER(TurnClasses), _i, _i, _i,
                                _vp, _i64, _vp, _vp, _i64, _vp]),

@@ -1149,6 +1149,20 @@ int ce2e_env_step(const ce2e_paths *paths, const int32_t *ref_idx, const float *
     return after_launch("k_env_done");
 }
 
+int ce2e_judge_done(int task, const float *obs, int64_t ld, const float *act_scaled, int V, int n_future,
+                    int v_light, int8_t *done_out, int64_t B, void *stream) {
+    int rc;
+    if ((rc = check_batch(B))) return rc;
+    if ((rc = check_task(task))) return rc;
+    if (B == 0) return CE2E_OK;
+    if (!obs || !act_scaled || !done_out) return fail(CE2E_ERR_NULL, "NULL argument");
+    if (V < 0 || V > CE2E_MAX_VEH || n_future < 0 || ld < 6 + 3 * (n_future + 1) + 4 * V)
+        return fail(CE2E_ERR_SHAPE, "bad V / n_future / ld");
+    k_env_done<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
+        make_dyn_consts(1.0 / 10.0), task, obs, ld, act_scaled, V, 6 + 3 * (n_future + 1), v_light, done_out, B);
+    return after_launch("k_env_done");
+}
+
 int ce2e_veh_predict(const float *veh_in, int64_t ld_in, const ce2e_turn_classes *turn, int V,
                      float *veh_out, int64_t ld_out, int64_t B, void *stream) {
     int rc;

@@ -191,6 +191,21 @@ class CrossroadEnd2end(object):
         self.obs[rows] = fresh
         self.ref_indexes[rows] = ref_dev
 
+    def _judge_done(self, obs=None, scaled_action=None):
+        """E2E:200-256 on the current (or given) post-step observations -> (done_type, done) for one
+        environment, (codes, done) tensors for a batch."""
+        obs = self.obs if obs is None else self.env_model._adopt(np.atleast_2d(np.asarray(obs, np.float32)))
+        act = self.action if scaled_action is None else to_device(np.atleast_2d(np.asarray(scaled_action, np.float32)))
+        B = obs.shape[0]
+        done = torch.empty((B,), dtype=torch.int8, device=obs.device)
+        _lib.check(_lib.load().ce2e_judge_done(_lib.TASK_ID[self.training_task], _ptr(obs), obs.stride(0) if B > 1 else
+                                               max(obs.stride(0), obs.shape[1]), _ptr(act.contiguous()), self.veh_num,
+                                               int(self.num_future_data), int(self.v_light), _ptr(done), B, _stream()))
+        if B == 1:
+            code = int(done.item())
+            return DONE_TYPES[code], int(code != 0)
+        return _wrap(done), _wrap(done != 0)
+
     # -- reference-named numeric helpers (batch-1 callers) ---------------------------------------
     def _ego_dynamics_dict(self):
         o = self.obs.numpy()[0]

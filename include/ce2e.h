@@ -147,6 +147,12 @@ int ce2e_env_step(const ce2e_paths *paths, const int32_t *ref_idx, const float *
                   float *obs_out, int64_t ld_out, float *out5, float *dict16, float *act_scaled_out,
                   int8_t *done_out, int64_t B, void *stream);
 
+/* CrossroadEnd2end._judge_done (E2E:200-256) with Traffic.collision_check (traffic.py:263-295) on
+ * observations obs [B,D] taken AFTER a step; act_scaled [B,2] = the scaled action of that step
+ * (its a_x fixes miu_r in the yaw-rate bound, E2E:167).  done_out as in ce2e_env_step.       */
+int ce2e_judge_done(int task, const float *obs, int64_t ld, const float *act_scaled, int V, int n_future,
+                    int v_light, int8_t *done_out, int64_t B, void *stream);
+
 /* EnvironmentModel.veh_predict (DM:394-427): veh_in/veh_out point at the first vehicle
  * column of each row ([B,4V] with ld_in / ld_out).                                        */
 int ce2e_veh_predict(const float *veh_in, int64_t ld_in, const ce2e_turn_classes *turn, int V,

@@ -15,7 +15,9 @@ What it restates (all citations into /root/reference/):
   dynamics_and_models.py:577-770  deal_with_phi_diff, ReferencePath
   endtoend_env_utils.py:14-46     constants and vehicle-mode tables
   endtoend_env_utils.py:73-104    judge_feasible
-  endtoend.py:150-283             ego corner points / r_bound / done logic / Gym-side post-ops
+  endtoend.py:132-283, 501-507    Gym step: action scaling, next ego state, ego dynamics (corner
+                                  points, r_bound), done logic, reward (gym_* functions)
+  traffic.py:263-295              two-circle collision check
 
 Numerics policy: tensors are fp32; + - * / sqrt are the
 IEEE fp32 ops NumPy performs (one rounding each, no FMA), in the association
@@ -619,38 +621,41 @@ DONE_CODES = ('not_done_yet', 'collision', 'break_road_constrain', 'deviate_too_
               'break_red_light', 'good_done')
 
 
-def gym_env_step(obs, actions_norm, task, ref_indexes, path_list, mode_list, num_future_data=0, v_light=0):
-    """One step of B independent SUMO-free CrossroadEnd2end environments, vectorised restatement of
-    endtoend.py:132-144 with the surrounding traffic advanced by the analytic model (veh_predict,
-    DM:394-427) in place of Traffic.sim_step, and every surrounding vehicle sized like the ego
-    (4.8 x 2.0) in Traffic.collision_check (traffic.py:263-295).
-
-    PARITY UNPINNED for the done logic: the reference's Gym class needs SUMO and cannot run here,
-    so this part is a restatement only (scalar Python in the reference -> float64 NumPy here).
-
-    Returns (next_obs [B,D] f32, reward [B] f32, done_code [B] int8, margin [B] f64) where margin
-    is the smallest slack of any threshold comparison that decided the row's code."""
-    obs = np.asarray(obs, dtype=f32)
-    B = obs.shape[0]
-    ntr = 3 * (num_future_data + 1)
-    scaled = action_transformation(actions_norm)                                    # E2E:258-267
-    reward = compute_rewards(obs, scaled, task, num_future_data)[0]                 # E2E:501-507
-    nxt, params = f_xu(obs[:, :6], scaled, 1 / 10)                                  # E2E:279
+def gym_next_ego_state(ego6, actions_norm):
+    """CrossroadEnd2end._action_transformation_for_end2end + _get_next_ego_state (E2E:258-283):
+    returns (scaled actions, next ego state with v_x floored at 0 and heading wrapped, tyre params)."""
+    scaled = action_transformation(actions_norm)
+    nxt, params = f_xu(np.asarray(ego6, dtype=f32)[:, :6], scaled, 1 / 10)          # E2E:279
     nxt = nxt.copy()
     nxt[:, 0] = np.where(nxt[:, 0] >= 0, nxt[:, 0], f32(0))                         # E2E:281
     nxt[:, 5] = np.array([deal_with_phi(float(p)) for p in nxt[:, 5]], dtype=f32)   # E2E:282
-    veh = veh_predict(obs[:, 6 + ntr:], mode_list)                                  # stands in for sim_step
-    trk = np.zeros((B, ntr), dtype=f32)
-    ref_indexes = np.asarray(ref_indexes)
-    for pi in range(len(path_list)):                                                # E2E:293-297
-        m = ref_indexes == pi
-        if m.any():
-            rp = ReferencePath(task, pi, path_list=path_list)
-            trk[m] = rp.tracking_error_vector(nxt[m, 3], nxt[m, 4], nxt[m, 5], nxt[m, 0], num_future_data)
-    next_obs = np.concatenate([nxt, trk, veh], 1).astype(f32)
+    return scaled, nxt, params
 
-    # ---- _judge_done (E2E:200-256), float64 like the reference's Python scalars ----
-    vx, r, x, y, phi = (nxt[:, i].astype(np.float64) for i in (0, 2, 3, 4, 5))
+
+def gym_ego_dynamics(nxt, params):
+    """CrossroadEnd2end._get_ego_dynamics (E2E:150-183): the four body corners [B,4,2] and r_bound
+    [B], float64 like the reference's Python scalars (legacy NumPy promotes float32-scalar x
+    Python-float to float64)."""
+    vx, x, y, phi = (np.asarray(nxt)[:, i].astype(np.float64) for i in (0, 3, 4, 5))
+    miu_r = np.asarray(params)[:, 3].astype(np.float64)
+    r_bound = miu_r * VEHICLE_PARAMS['g'] / (np.abs(vx) + 1e-8)                      # E2E:167
+    corners = []
+    for lx, ly in ((L / 2, W / 2), (L / 2, -W / 2), (-L / 2, W / 2), (-L / 2, -W / 2)):   # E2E:171-177
+        px, py = rotate_and_shift_coordination(lx, ly, 0, -x, -y, -phi)
+        corners.append(np.stack([px, py], 1))
+    return np.stack(corners, 1), r_bound
+
+
+def gym_judge_done(nxt, params, delta_y, veh_after, task, v_light=0):
+    """CrossroadEnd2end._judge_done (E2E:200-256) with Traffic.collision_check (traffic.py:263-295,
+    every surrounding vehicle sized L x W like the ego).  veh_after [B, 4V] = vehicles after the
+    traffic step; v_light scalar or [B].  Returns (code [B] int8 indexing DONE_CODES, margin [B]
+    = smallest slack of the threshold comparisons evaluated before the row's code was decided)."""
+    nxt = np.asarray(nxt, dtype=f32)
+    veh = np.asarray(veh_after, dtype=f32).reshape(len(nxt), -1)
+    B = len(nxt)
+    r, x, y, phi = (nxt[:, i].astype(np.float64) for i in (2, 3, 4, 5))
+    v_light = np.broadcast_to(np.asarray(v_light), (B,))
     code = np.zeros(B, np.int8)
     margin = np.full(B, np.inf)
 
@@ -660,17 +665,15 @@ def gym_env_step(obs, actions_norm, task, ref_indexes, path_list, mode_list, num
         margin = np.where(open_, np.minimum(margin, slack), margin)
         code = np.where(open_ & cond, np.int8(c), code)
 
-    # collision_check (traffic.py:263-295)
-    lw = (L - W) / 2
+    lw = (L - W) / 2                                                                # traffic.py:270-274
     ex0, ey0 = x + np.cos(phi / 180 * np.pi) * lw, y + np.sin(phi / 180 * np.pi) * lw
     ex1, ey1 = x - np.cos(phi / 180 * np.pi) * lw, y - np.sin(phi / 180 * np.pi) * lw
     hit = np.zeros(B, bool)
     slack = np.full(B, np.inf)
-    thr = ((W + W) / 2 + 0.5) ** 2
-    V = veh.shape[1] // 4
-    for j in range(V):
+    thr = ((W + W) / 2 + 0.5) ** 2                                                  # traffic.py:284
+    for j in range(veh.shape[1] // 4):
         vxx, vyy, vph = (veh[:, 4 * j + k].astype(np.float64) for k in (0, 1, 3))
-        gate = (np.abs(vxx - x) < 10) & (np.abs(vyy - y) < 10)
+        gate = (np.abs(vxx - x) < 10) & (np.abs(vyy - y) < 10)                      # traffic.py:278
         slack = np.minimum(slack, np.minimum(np.abs(np.abs(vxx - x) - 10), np.abs(np.abs(vyy - y) - 10)))
         sx0, sy0 = vxx + np.cos(vph / 180 * np.pi) * lw, vyy + np.sin(vph / 180 * np.pi) * lw
         sx1, sy1 = vxx - np.cos(vph / 180 * np.pi) * lw, vyy - np.sin(vph / 180 * np.pi) * lw
@@ -679,19 +682,17 @@ def gym_env_step(obs, actions_norm, task, ref_indexes, path_list, mode_list, num
             hit |= gate & (d2 < thr)
             slack = np.minimum(slack, np.where(gate, np.abs(d2 - thr), np.inf))
     decide(hit, slack, 1)
-    # _break_road_constrain: four corners (E2E:171-177) through judge_feasible (EU:73-104)
-    ok = np.ones(B, bool)
+    corners, r_bound = gym_ego_dynamics(nxt, params)
+    ok = np.ones(B, bool)                                                           # E2E:227-229
     slack = np.full(B, np.inf)
-    for lx, ly in ((L / 2, W / 2), (L / 2, -W / 2), (-L / 2, W / 2), (-L / 2, -W / 2)):
-        px, py = rotate_and_shift_coordination(lx, ly, 0, -x, -y, -phi)
+    for k in range(4):
+        px, py = corners[:, k, 0], corners[:, k, 1]
         ok &= np.array([judge_feasible(a, b, task) for a, b in zip(px, py)], bool)
         for edge in (-25., 25., 0., LANE_WIDTH, 2 * LANE_WIDTH, 3 * LANE_WIDTH, -3 * LANE_WIDTH):
             slack = np.minimum(slack, np.minimum(np.abs(px - edge), np.abs(py - edge)))
     decide(~ok, slack, 2)
-    dy = next_obs[:, 6].astype(np.float64)
+    dy = np.asarray(delta_y).astype(np.float64)
     decide(np.abs(dy) > 15, np.abs(np.abs(dy) - 15), 3)                              # E2E:223-225
-    miu_r = params[:, 3].astype(np.float64)
-    r_bound = miu_r * VEHICLE_PARAMS['g'] / (np.abs(vx) + 1e-8)                      # E2E:167
     decide(~((-r_bound < r) & (r < r_bound)), np.abs(np.abs(r) - r_bound), 4)       # E2E:231-242
     decide((v_light != 0) & (y > -CROSSROAD_SIZE / 2) & (task != 'right'), np.abs(y + CROSSROAD_SIZE / 2), 5)
     road = LANE_NUMBER * LANE_WIDTH
@@ -705,4 +706,31 @@ def gym_env_step(obs, actions_norm, task, ref_indexes, path_list, mode_list, num
         goal = (y > CROSSROAD_SIZE / 2 + 10) & (0 < x) & (x < road)
         slack = np.minimum(np.abs(y - 35), np.minimum(np.abs(x), np.abs(x - road)))
     decide(goal, slack, 6)
+    return code, margin
+
+
+def gym_env_step(obs, actions_norm, task, ref_indexes, path_list, mode_list, num_future_data=0, v_light=0):
+    """One step of B independent SUMO-free CrossroadEnd2end environments: vectorised restatement of
+    endtoend.py:132-144 with the surrounding traffic advanced by the analytic model (veh_predict,
+    DM:394-427) in place of Traffic.sim_step.  The ego update, ego dynamics and done logic are
+    pinned against the unmodified reference methods (tests/golden/make_golden_env.py ->
+    tests/golden/env_*.npz, tests/test_oracle_golden.py); the traffic substitution is this
+    project's (the reference needs a SUMO process).
+
+    Returns (next_obs [B,D] f32, reward [B] f32, done_code [B] int8, margin [B] f64)."""
+    obs = np.asarray(obs, dtype=f32)
+    B = obs.shape[0]
+    ntr = 3 * (num_future_data + 1)
+    scaled, nxt, params = gym_next_ego_state(obs[:, :6], actions_norm)
+    reward = compute_rewards(obs, scaled, task, num_future_data)[0]                 # E2E:501-507
+    veh = veh_predict(obs[:, 6 + ntr:], mode_list)                                  # stands in for sim_step
+    trk = np.zeros((B, ntr), dtype=f32)
+    ref_indexes = np.asarray(ref_indexes)
+    for pi in range(len(path_list)):                                                # E2E:293-297
+        m = ref_indexes == pi
+        if m.any():
+            rp = ReferencePath(task, pi, path_list=path_list)
+            trk[m] = rp.tracking_error_vector(nxt[m, 3], nxt[m, 4], nxt[m, 5], nxt[m, 0], num_future_data)
+    next_obs = np.concatenate([nxt, trk, veh], 1).astype(f32)
+    code, margin = gym_judge_done(nxt, params, next_obs[:, 6], veh, task, v_light)
     return next_obs, reward, code, margin

@@ -135,3 +135,27 @@ def test_auto_reset(e2e):
         # rows that were reset start on their path again: tracking error is that of a fresh pose
         assert np.abs(o[done.numpy(), 6]).max(initial=0.0) < 1.0
     assert n_done > 0
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_judge_done_against_reference_methods(e2e, task):
+    """k_env_done on the inputs of the golden vectors made by the UNMODIFIED reference methods
+    (tests/golden/make_golden_env.py): next ego state bit-exact except x, y (sin/cos), done codes
+    equal wherever the oracle's decision slack exceeds 1e-3."""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, 'env_%s.npz' % task), allow_pickle=False))
+    N, V = g['obs'].shape[0], orc.VEH_NUM[task]
+    env = e2e.CrossroadEnd2end(task, num_envs=N)
+    nxt, par = env.dynamics.prediction(g['obs'][:, :6], g['scaled'], 10)
+    nxt = nxt.numpy()
+    assert np.allclose(nxt[:, 1:5], g['next_ego'][:, 1:5], rtol=1e-5, atol=1e-5)
+    after = np.concatenate([g['next_ego'], g['obs'][:, 6:9], g['veh_after'].reshape(N, -1)], 1).astype(np.float32)
+    _, margin = orc.gym_judge_done(g['next_ego'], g['params'], g['obs'][:, 6], g['veh_after'], task, g['v_light'])
+    codes = {}
+    for vl in (0, 1):
+        env.v_light = vl
+        codes[vl] = env._judge_done(after, g['scaled'])[0].numpy()
+    got = np.where(g['v_light'] != 0, codes[1], codes[0])
+    ok = margin > 1e-3
+    assert ok.mean() > 0.95 and (got[ok] == g['done_code'][ok]).all()

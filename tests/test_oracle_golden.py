@@ -162,3 +162,30 @@ def test_rollout(task, tag, golden_task):
     if mode == 'training':
         # ref_index 3 matches no path -> zero tracking columns (DM:342-353)
         assert ref[0] == 3 and np.abs(g['ro_%s_obs' % tag][:, 0, 6:9 + 3 * n]).max() == 0
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_gym_side_against_reference_methods(task):
+    """gym_next_ego_state / gym_ego_dynamics / gym_judge_done against the UNMODIFIED reference
+    methods (CrossroadEnd2end._get_next_ego_state, _get_ego_dynamics, _judge_done, compute_reward,
+    Traffic.collision_check) run by tests/golden/make_golden_env.py."""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, 'env_%s.npz' % task), allow_pickle=False))
+    scaled, nxt, params = orc.gym_next_ego_state(g['obs'][:, :6], g['act'])
+    _same(scaled, g['scaled'], 'scaled action')
+    _same(nxt, g['next_ego'], 'next ego state')
+    _same(params, g['params'], 'tyre params')
+    corners, r_bound = orc.gym_ego_dynamics(nxt, params)
+    # the reference mixes np.float32 scalars with Python floats here, so its own result depends on
+    # the NumPy version (float64 before NEP 50, float32 after); the goldens were made with NumPy 2
+    assert np.allclose(corners, g['corners'], rtol=0, atol=1e-5)
+    fin = np.isfinite(g['r_bound'])
+    assert np.allclose(r_bound[fin], g['r_bound'][fin], rtol=1e-6) and (np.isfinite(r_bound) == fin).all()
+    rew = orc.compute_rewards(g['obs'], scaled, task)[0]
+    _same(rew, g['reward'], 'reward')
+    code, margin = orc.gym_judge_done(nxt, params, g['obs'][:, 6], g['veh_after'], task, g['v_light'])
+    assert (code == g['done_code']).all(), np.flatnonzero(code != g['done_code'])
+    assert set(np.unique(code).tolist()) >= {0, 1, 2, 3, 4, 6}
+    if task != 'right':
+        assert (code == 5).any()
