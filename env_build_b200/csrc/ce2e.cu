@@ -205,8 +205,10 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+// Block-wide named barrier, NON-aligned form: the warps of a block reach it from two different
+// places (inside their first tile, or after the tile loop when they own no tile).
 __device__ __forceinline__ void named_barrier_sync(int id, int threads) {
-    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
+    asm volatile("barrier.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v) : "memory");
