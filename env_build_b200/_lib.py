@@ -37,6 +37,7 @@ SIGNATURES = {
     'ce2e_version': (_i, []),
     'ce2e_last_error': (_c.c_char_p, []),
     'ce2e_launch_count': (_i64, []),
+    'ce2e_set_fast_trig': (_i, [_i]),
     'ce2e_paths_create': (_i, [_i, _i, _c.POINTER(_c.c_int32), _c.POINTER(_vp), _c.POINTER(_vp),
                                _c.POINTER(_vp), _c.POINTER(_vp)]),
     'ce2e_paths_destroy': (_i, [_vp]),
@@ -118,3 +119,8 @@ def make_turn_classes(classes):
     for i, c in enumerate(classes):
         t.tc[i] = int(c)
     return t
+
+
+def set_fast_trig(enable):
+    """See ce2e_set_fast_trig in include/ce2e.h (off by default).  Returns the previous setting."""
+    return bool(load().ce2e_set_fast_trig(int(bool(enable))))

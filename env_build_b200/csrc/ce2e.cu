@@ -34,6 +34,7 @@ namespace {
 thread_local char g_err[512] = "";
 thread_local int64_t g_launches = 0;
 bool g_use_pdl = getenv("CE2E_NO_PDL") == nullptr;
+bool g_fast_trig = false;
 
 int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -232,11 +233,12 @@ __device__ __forceinline__ void pair_gate(float ex, float ey, float px, float py
 
 // One surrounding vehicle of one row: gate its four circle pairs against the ego circles and
 // return its predicted state (DM:218-229, DM:405-427).  Branch free.
-template <bool REW, bool NEXT>
+template <bool REW, bool NEXT, bool FAST>
 __device__ __forceinline__ float4 vehicle_step(float4 v, const Circles &ec, int tc, unsigned &qa) {
     const float th = deg2rad(v.w);
     float vs, vc;
-    sincos_cw(th, vs, vc);
+    if (FAST) sincos_mufu(th, vs, vc);
+    else sincos_cw(th, vs, vc);
     if (REW) {
         const Circles w = circle_centres(v.x, v.y, vs, vc);
         pair_gate(ec.fx, ec.fy, w.fx, w.fy, qa);
@@ -276,7 +278,7 @@ __device__ __forceinline__ void candidate_range(const GridView &gv, int p, int n
 //                  end of the tile, in the reference's order (vehicle, ego circle, vehicle circle).
 //                  veh2veh = (sum over the first half) + (sum over the second half): a fixed
 //                  order, independent of the batch size.
-template <bool REW, bool NEXT>
+template <bool REW, bool NEXT, bool FAST = false>
 __global__ void __launch_bounds__(STEP_THREADS, 2)
 k_model_step(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -481,14 +483,14 @@ k_model_step(const __grid_constant__ StepParams P) {
 #pragma unroll
                 for (int e = 0; e < VPL; e += 2) {          // two independent vehicles at a time
                     float4 v0 = slot[e ^ swz], v1 = slot[(e + 1) ^ swz];
-                    v0 = vehicle_step<REW, NEXT>(v0, ec, P.turn.tc[j0 + e], qa);
-                    v1 = vehicle_step<REW, NEXT>(v1, ec, P.turn.tc[j0 + e + 1], qa);
+                    v0 = vehicle_step<REW, NEXT, FAST>(v0, ec, P.turn.tc[j0 + e], qa);
+                    v1 = vehicle_step<REW, NEXT, FAST>(v1, ec, P.turn.tc[j0 + e + 1], qa);
                     if (NEXT) { slot[e ^ swz] = v0; slot[(e + 1) ^ swz] = v1; }
                 }
             } else {
                 for (int e = 0; e < VPL; ++e) {
                     if (j0 + e < j_end) {
-                        const float4 nv = vehicle_step<REW, NEXT>(slot[e ^ swz], ec, P.turn.tc[j0 + e], qa);
+                        const float4 nv = vehicle_step<REW, NEXT, FAST>(slot[e ^ swz], ec, P.turn.tc[j0 + e], qa);
                         if (NEXT && j0 + e < P.V_out) slot[e ^ swz] = nv;
                     }
                 }
@@ -576,11 +578,13 @@ int launch_model_step(StepParams &P, cudaStream_t st) {
                     di->max_smem_optin);
     void (*kern)(const StepParams) = nullptr;
     const bool rew = P.flags & F_REWARD, next = P.flags & F_NEXT;
-    if (rew && next) kern = k_model_step<true, true>;
+    const bool fast = g_fast_trig && rew && next;
+    if (fast) kern = k_model_step<true, true, true>;
+    else if (rew && next) kern = k_model_step<true, true>;
     else if (rew) kern = k_model_step<true, false>;
     else kern = k_model_step<false, true>;
-    static thread_local size_t smem_set[3] = {0, 0, 0};
-    size_t &set = smem_set[rew && next ? 0 : rew ? 1 : 2];
+    static thread_local size_t smem_set[4] = {0, 0, 0, 0};
+    size_t &set = smem_set[fast ? 3 : rew && next ? 0 : rew ? 1 : 2];
     if (smem > set) {
         CE2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         set = smem;
@@ -935,6 +939,11 @@ int model_step_common(const ce2e_paths *paths, int task, int path_index, const i
 extern "C" {
 
 int ce2e_version(void) { return CE2E_VERSION; }
+int ce2e_set_fast_trig(int enable) {
+    const int old = g_fast_trig;
+    g_fast_trig = enable != 0;
+    return old;
+}
 const char *ce2e_last_error(void) { return g_err; }
 int64_t ce2e_launch_count(void) { return g_launches; }
 

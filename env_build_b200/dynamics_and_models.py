@@ -39,24 +39,37 @@ def _wrap(t):
     return t.as_subclass(DeviceTensor)
 
 
+_CUDA_CHECKED = False
+_RAW_STREAM = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def _device():
-    if not torch.cuda.is_available():
-        raise RuntimeError('env_build_b200 needs a CUDA device: the model path has no CPU fallback')
+    global _CUDA_CHECKED
+    if not _CUDA_CHECKED:
+        if not torch.cuda.is_available():
+            raise RuntimeError('env_build_b200 needs a CUDA device: the model path has no CPU fallback')
+        _CUDA_CHECKED = True
     return torch.device('cuda', torch.cuda.current_device())
+
+
+def _raw(t):
+    """A plain torch.Tensor view of `t` (DeviceTensor's __torch_function__ costs microseconds per op)."""
+    return t.as_subclass(torch.Tensor) if type(t) is not torch.Tensor else t
 
 
 def to_device(x, dtype=torch.float32):
     """NumPy / list / torch (any device) -> CUDA tensor of `dtype` (no copy if already there)."""
-    dev = _device()
     if isinstance(x, torch.Tensor):
-        t = x.detach()
-        if isinstance(t, DeviceTensor):
-            t = t.as_subclass(torch.Tensor)
-        return t.to(device=dev, dtype=dtype)
-    return torch.as_tensor(np.asarray(x), device=dev).to(dtype)
+        t = _raw(x)
+        if t.is_cuda and t.dtype == dtype and not t.requires_grad:
+            return t
+        return t.detach().to(device=_device(), dtype=dtype)
+    return torch.as_tensor(np.asarray(x), device=_device()).to(dtype)
 
 
 def _stream():
+    if _RAW_STREAM is not None:
+        return ctypes.c_void_p(_RAW_STREAM(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -318,11 +331,11 @@ class EnvironmentModel(object):  # all tensors
         self.mode = mode
         self.vehicle_dynamics = VehicleDynamics()
         self.base_frequency = 10.
-        self.obses = None
+        self._obs = None                 # raw padded device tensor behind the `obses` attribute
+        self._ref = None
         self.ego_params = None
         self.actions = None
         self.ref_path = ReferencePath(self.task)
-        self.ref_indexes = None
         self.num_future_data = num_future_data
         self.exp_v = EXPECTED_V
         self.reward_info = None
@@ -335,6 +348,24 @@ class EnvironmentModel(object):  # all tensors
     def set_veh_mode_list(self, modes):
         self.veh_mode_list = list(modes)
         self._turn = _lib.make_turn_classes([turn_class(m) for m in self.veh_mode_list])
+        self._turn_ref = ctypes.byref(self._turn)
+
+    @property
+    def obses(self):
+        """The current observations (DM:100), a CUDA tensor in the padded row layout."""
+        return None if self._obs is None else _wrap(self._obs)
+
+    @obses.setter
+    def obses(self, value):
+        self._obs = None if value is None else self._adopt(value)
+
+    @property
+    def ref_indexes(self):
+        return None if self._ref is None else _wrap(self._ref)
+
+    @ref_indexes.setter
+    def ref_indexes(self, value):
+        self._ref = None if value is None else to_device(value, torch.int32).reshape(-1).contiguous()
 
     @property
     def _veh_off(self):
@@ -360,47 +391,53 @@ class EnvironmentModel(object):  # all tensors
         return (obses.shape[1] - self._veh_off) // self.per_veh_info_dim
 
     def reset(self, obses, ref_indexes=None):  # input are all tensors
-        self.obses = _wrap(self._adopt(obses))
-        self.ref_indexes = None if ref_indexes is None else \
-            _wrap(to_device(ref_indexes, torch.int32).reshape(-1).contiguous())
+        self.obses = obses
+        self.ref_indexes = ref_indexes
         self.actions = None
         self.reward_info = None
 
     def add_traj(self, obses, path_index):
-        self.obses = _wrap(self._adopt(obses))
+        self.obses = obses
         self.ref_path.set_path(path_index)
 
     def _path_args(self, B):
         if self.mode != 'training':
             return int(self.ref_path.ref_index), None
-        if self.ref_indexes is None:
+        ref = self._ref
+        if ref is None:
             raise ValueError("mode='training' needs per-row ref_indexes (reset(obses, ref_indexes))")
-        if self.ref_indexes.shape[0] != B:
-            raise ValueError('ref_indexes has %d entries for %d rows' % (self.ref_indexes.shape[0], B))
-        return 0, self.ref_indexes
+        if ref.shape[0] != B:
+            raise ValueError('ref_indexes has %d entries for %d rows' % (ref.shape[0], B))
+        return 0, ref
 
     # -- the hot call -----------------------------------------------------------------------
     def rollout_out(self, actions):  # obses and actions are tensors, think of actions are in range [-1, 1]
         """DM:118-126: one fused launch (ce2e_rollout_step)."""
-        obs = self.obses
-        B = obs.shape[0]
-        act = _rows(to_device(actions), 'actions', 2).contiguous()
-        if act.shape[0] != B:
-            raise ValueError('actions have %d rows for %d observations' % (act.shape[0], B))
-        V_in, V_out = self._num_veh(obs), len(self.veh_mode_list)
+        obs = self._obs
+        B, D = obs.shape
+        act = to_device(actions)
+        if act.dim() != 2 or act.shape[1] != 2 or act.shape[0] != B:
+            raise ValueError('actions must have shape [%d, 2], got %s' % (B, tuple(act.shape)))
+        if not act.is_contiguous():
+            act = act.contiguous()
+        veh_off = self._veh_off
+        V_in, V_out = (D - veh_off) // 4, len(self.veh_mode_list)
         if V_out > V_in:
             raise ValueError('observations hold %d vehicles but the mode list has %d' % (V_in, V_out))
         path_index, ref = self._path_args(B)
-        nxt = padded_rows(B, self._veh_off + 4 * V_out, self._veh_off, obs.device)
-        out5 = torch.empty((5, B), dtype=torch.float32, device=obs.device)
-        scaled = torch.empty((B, 2), dtype=torch.float32, device=obs.device)
-        _lib.check(_lib.load().ce2e_rollout_step(self.ref_path.handle, path_index, _ptr(ref), _ptr(obs), _ld(obs),
-                                                 _ptr(act), ctypes.byref(self._turn), V_in, V_out,
-                                                 int(self.num_future_data), _ptr(nxt), _ld(nxt), _ptr(out5),
-                                                 _ptr(scaled), B, _stream()))
+        dev = obs.device
+        nxt = padded_rows(B, veh_off + 4 * V_out, veh_off, dev)
+        out5 = torch.empty((5, B), dtype=torch.float32, device=dev)
+        scaled = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        rc = _lib.load().ce2e_rollout_step(self.ref_path.handle, path_index, _ptr(ref), obs.data_ptr(), _ld(obs),
+                                           act.data_ptr(), self._turn_ref, V_in, V_out, int(self.num_future_data),
+                                           nxt.data_ptr(), _ld(nxt), out5.data_ptr(), scaled.data_ptr(), B, _stream())
+        if rc:
+            _lib.check(rc)
         self.actions = _wrap(scaled)
-        self.obses = _wrap(nxt)
-        return (self.obses,) + tuple(_wrap(out5[i]) for i in range(5))
+        self._obs = nxt
+        self.last_out5 = out5            # [5, B]: the five returned vectors as one tensor
+        return (_wrap(nxt),) + tuple(_wrap(t) for t in out5.unbind(0))
 
     def _action_transformation_for_end2end(self, actions):  # [-1, 1]
         act = _rows(to_device(actions), 'actions', 2).contiguous()

@@ -60,6 +60,12 @@ typedef struct ce2e_paths ce2e_paths;
 int ce2e_version(void);
 const char *ce2e_last_error(void);
 
+/* Process-wide option, default 0.  enable != 0: ce2e_rollout_step takes sin / cos of the SURROUNDING
+ * VEHICLES' headings (DM:220-224, DM:409-410) from the special-function unit (abs. error <= 2^-21.4
+ * instead of <= 1.5 ulp).  Results stay inside the 1e-5 parity tolerance; everything else is
+ * unchanged.  Returns the previous setting.                                                   */
+int ce2e_set_fast_trig(int enable);
+
 /* Number of CUDA kernels this library has launched from the calling thread since load. */
 int64_t ce2e_launch_count(void);
 

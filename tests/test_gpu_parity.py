@@ -444,3 +444,32 @@ def test_edge_cases_and_errors(dm):
     m.add_traj(bad, 0)
     r = m.rollout_out(np.array([[0.0, 0.0]], np.float32))
     assert np.isnan(r[0].numpy()[0, 3])
+
+
+def test_fast_trig_option_within_tolerance(dm):
+    """ce2e_set_fast_trig: vehicle sin/cos from the special-function unit stays inside 1e-5."""
+    from env_build_b200 import _lib
+    from env_build_b200 import synthetic as syn
+    rng = np.random.default_rng(9)
+    task, B, V = 'left', 20000, 32
+    model = dm.EnvironmentModel(task, mode='training', veh_mode_list=tiled(task, V))
+    ref = syn.make_ref_indexes(rng, B)
+    obs = syn.make_obs(rng, B, task, V, model.ref_path.path_list, ref)
+    act = syn.make_actions(rng, 1, B)[0]
+    model.reset(obs, ref)
+    exact = [r.numpy() for r in model.rollout_out(act)]
+    assert _lib.set_fast_trig(True) is False
+    try:
+        model.reset(obs, ref)
+        fast = [r.numpy() for r in model.rollout_out(act)]
+    finally:
+        assert _lib.set_fast_trig(False) is True
+    sc = orc.action_transformation(act)
+    want5 = orc.compute_rewards(obs, sc, task)[:5]
+    for a, b in zip(fast[1:], want5):
+        close(a, b)
+    om = orc.EnvironmentModel(task, mode='training', path_list=model.ref_path.path_list, veh_mode_list=tiled(task, V))
+    om.reset(obs, ref)
+    close(fast[0][:, 9:], om.compute_next_obses(obs, sc)[:, 9:])
+    bits_equal(fast[0][:, :9], exact[0][:, :9])                 # the ego path is untouched
+    print('fast-trig max |dx| vs exact kernel: %.3g' % np.abs(fast[0] - exact[0]).max())
