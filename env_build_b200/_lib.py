@@ -56,6 +56,8 @@ SIGNATURES = {
     'ce2e_veh_predict': (_i, [_vp, _i64, _c.POINTER(TurnClasses), _i, _vp, _i64, _i64, _vp]),
     'ce2e_rollout_step': (_i, [_vp, _i, _vp, _vp, _i64, _vp, _c.POINTER(TurnClasses), _i, _i, _i,
                                _vp, _i64, _vp, _vp, _i64, _vp]),
+    'ce2e_rollout_step_backward': (_i, [_vp, _i, _vp, _vp, _i64, _vp, _i, _i, _vp, _i64, _vp, _vp, _i64, _vp, _i64,
+                                        _vp]),
     'ce2e_ss': (_i, [_vp, _i64, _vp, _i64, _i, _i, _d, _vp, _i64, _vp]),
 }
 

@@ -869,6 +869,200 @@ __global__ void k_env_done(const __grid_constant__ DynConsts K, int task, const 
     done[i] = (int8_t)code;
 }
 
+// ------------------------------------------------------------------------------------------
+// backward of one rollout_out step
+// ------------------------------------------------------------------------------------------
+// Vector-Jacobian product of EnvironmentModel.rollout_out (DM:118-126) as TensorFlow's autodiff
+// defines it in the reference: vehicle columns carry tf.stop_gradient (DM:195, DM:331, DM:402), the
+// closest-waypoint index is an integer (tf.argmin / tf.gather: the reference point is a constant),
+// tf.where passes the gradient of the selected branch, tf.clip_by_value passes it inside the
+// closed interval.  One thread per row; the forward intermediates are recomputed.
+//   inputs : obs_in, act_norm (the forward inputs), upstream gradients g_next [B, 9+3n] (d loss /
+//            d next ego + next tracking columns) and g_out5 [5, B]
+//   outputs: g_obs [B, 9+3n] (ego + tracking columns of obs_in; the future-preview tracking columns
+//            only feed nothing and get 0), g_act [B, 2] (w.r.t. the NORMALISED actions)
+__device__ __forceinline__ void road_terms_grad(int task, float px, float py, float w_tr, float w_re,
+                                                float &gpx, float &gpy) {
+    // d/d(px, py) of the four hinge^2 terms of road_terms(); w_tr / w_re weight the training / real sums
+    if (task == 0) {
+        const bool before = py < -CE2E_HALF, after = px < -CE2E_HALF;
+        const float g1 = px - 1.0f, g2 = (CE2E_LW - px) - 1.0f, g3 = (CE2E_LW3 - py) - 1.0f, g4 = (py - 0.0f) - 1.0f;
+        const float w = w_tr + w_re;
+        if (before && px < 1.0f) gpx += w * 2.0f * g1;
+        if (before && (CE2E_LW - px) < 1.0f) gpx -= w * 2.0f * g2;
+        if (px < 0.0f && (CE2E_LW3 - py) < 1.0f) gpy -= w_tr * 2.0f * g3;
+        if (after && (CE2E_LW3 - py) < 1.0f) gpy -= w_re * 2.0f * g3;
+        if (after && (py - 0.0f) < 1.0f) gpy += w * 2.0f * g4;
+    } else if (task == 1) {
+        const bool before = py < -CE2E_HALF, after = py > CE2E_HALF;
+        const float g1 = (px - CE2E_LW) - 1.0f, g2 = (CE2E_LW2 - px) - 1.0f, g3 = (CE2E_LW3 - px) - 1.0f, g4 = (px - 0.0f) - 1.0f;
+        const float w = w_tr + w_re;
+        if (before && (px - CE2E_LW) < 1.0f) gpx += w * 2.0f * g1;
+        if (before && (CE2E_LW2 - px) < 1.0f) gpx -= w * 2.0f * g2;
+        if (after && (CE2E_LW3 - px) < 1.0f) gpx -= w * 2.0f * g3;
+        if (after && (px - 0.0f) < 1.0f) gpx += w * 2.0f * g4;
+    } else {
+        const bool before = py < -CE2E_HALF, after = px > CE2E_HALF;
+        const float g1 = (px - CE2E_LW2) - 1.0f, g2 = (CE2E_LW3 - px) - 1.0f, g3 = (0.0f - py) - 1.0f, g4 = (py - (-CE2E_LW3)) - 1.0f;
+        const float w = w_tr + w_re;
+        if (before && (px - CE2E_LW2) < 1.0f) gpx += w * 2.0f * g1;
+        if (before && (CE2E_LW3 - px) < 1.0f) gpx -= w * 2.0f * g2;
+        if (after && (0.0f - py) < 1.0f) gpy -= w * 2.0f * g3;
+        if (after && (py - (-CE2E_LW3)) < 1.0f) gpy += w * 2.0f * g4;
+    }
+}
+
+__device__ __forceinline__ void pair_grad(float ex, float ey, float px, float py, float w_tr, float w_re,
+                                          float &gx, float &gy) {
+    const float dx = ex - px, dy = ey - py;
+    const float dd = dx * dx + dy * dy;
+    if (dd < 12.25f && dd > 0.0f) {
+        const float d = __fsqrt_rn(dd);
+        float k = 0.0f;
+        if (d - 3.5f < 0.0f) k += w_tr * 2.0f * (d - 3.5f);
+        if (d - 2.5f < 0.0f) k += w_re * 2.0f * (d - 2.5f);
+        k = k / d;
+        gx += k * dx;
+        gy += k * dy;
+    }
+}
+
+__global__ void k_model_step_bwd(const __grid_constant__ PathView pv, const __grid_constant__ GridView gv,
+                                 const __grid_constant__ DynConsts K, int task, int path_index,
+                                 const int32_t *__restrict__ ref_idx, const float *__restrict__ obs,
+                                 int64_t ld, const float *__restrict__ act_norm, int V, int n_future,
+                                 const float *__restrict__ g_next, int64_t ld_gn,
+                                 const float *__restrict__ g_out5, float *__restrict__ g_obs, int64_t ld_go,
+                                 float *__restrict__ g_act, int64_t B) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float *o = obs + i * ld;
+    const int n_trk = 3 * (n_future + 1);
+    const float vx = o[0], vy = o[1], r = o[2], x = o[3], y = o[4], phi_deg = o[5];
+    const float a0 = act_norm[2 * i], a1 = act_norm[2 * i + 1];
+    float steer, a_x;
+    action_transform(a0, a1, steer, a_x);
+    const float m0 = (a0 >= -1.05f && a0 <= 1.05f) ? 0.4f : 0.0f;        // d steer / d a0
+    const float m1 = (a1 >= -1.05f && a1 <= 1.05f) ? 2.25f : 0.0f;       // d a_x / d a1
+    const float D2R = CE2E_PI32 / 180.0f;
+    const float phi = deg2rad(phi_deg);
+    float s, c;
+    sincos_cw(phi, s, c);
+    const float gR = g_out5[i], gPtr = g_out5[B + i], gPre = g_out5[2 * B + i], gV2V = g_out5[3 * B + i],
+                gV2R = g_out5[4 * B + i];
+
+    // gradients w.r.t. (vx, vy, r, x, y, phi_deg, steer, a_x) and the tracking columns
+    float gvx = 0.f, gvy = 0.f, gr = 0.f, gx = 0.f, gy = 0.f, gphi = 0.f, gsteer = 0.f, gax = 0.f;
+    // ---- rewards (DM:198-207, 297-298)
+    const float g_dy = gR * (-1.6f * o[6]);
+    const float g_dphi = gR * (-60.0f * D2R * D2R * o[7]);
+    const float g_dv = gR * (-0.1f * o[8]);
+    gr += gR * (-0.04f * r);
+    gsteer += gR * (-10.0f * steer);
+    gax += gR * (-0.1f * a_x);
+    // ---- collision and road penalties through the ego circle centres (DM:210-295)
+    {
+        const Circles ec = circle_centres(x, y, s, c);
+        const float w_tr = gPtr, w_re_v = gPre + gV2V, w_re_r = gPre + gV2R;
+        float gfx = 0.f, gfy = 0.f, grx = 0.f, gry = 0.f;
+        const float *veh = o + 6 + n_trk;
+        for (int j = 0; j < V; ++j) {
+            const float *v = veh + 4 * j;
+            float vs, vc;
+            sincos_cw(deg2rad(v[3]), vs, vc);
+            const Circles w = circle_centres(v[0], v[1], vs, vc);
+            pair_grad(ec.fx, ec.fy, w.fx, w.fy, w_tr, w_re_v, gfx, gfy);
+            pair_grad(ec.fx, ec.fy, w.rx, w.ry, w_tr, w_re_v, gfx, gfy);
+            pair_grad(ec.rx, ec.ry, w.fx, w.fy, w_tr, w_re_v, grx, gry);
+            pair_grad(ec.rx, ec.ry, w.rx, w.ry, w_tr, w_re_v, grx, gry);
+        }
+        road_terms_grad(task, ec.fx, ec.fy, w_tr, w_re_r, gfx, gfy);
+        road_terms_grad(task, ec.rx, ec.ry, w_tr, w_re_r, grx, gry);
+        gx += gfx + grx;
+        gy += gfy + gry;
+        // F = (x + l c, y + l s), R = (x - l c, y - l s);  d/dphi_deg = D2R * d/dtheta
+        gphi += D2R * CE2E_LWS * ((-s) * gfx + c * gfy + s * grx - c * gry);
+    }
+    // ---- next observation (DM:322-353)
+    const float *gn = g_next + i * ld_gn;
+    float nxt[6];
+    f_xu_next(K, vx, vy, r, x, y, phi, s, c, steer, a_x, nxt);
+    const float vx_raw = nxt[0];
+    nxt[0] = fminf(fmaxf(vx_raw, 0.0f), 35.0f);
+    float g_n[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g_n[k] = gn[k];
+    int p = ref_idx ? ref_idx[i] : path_index;
+    if (p >= 0 && p < pv.n_paths) {                                     // tracking' = T(x', y', phi', vx')
+        const float2 *t_xy = pv.xy + (size_t)p * pv.stride;
+        int k0, k1, bi;
+        float best;
+        candidate_range(gv, p, (pv.N[p] + 1) & ~1, nxt[3], nxt[4], k0, k1);
+        scan_min(t_xy, k0, k1, nxt[3], nxt[4], best, bi);
+        const float2 w = t_xy[bi];
+        const float ex = nxt[3], ey = nxt[4];
+        float ddx = 0.f, ddy = 0.f;                                     // d(two2one)/d(ex, ey) = -d(delta)
+        if (task == 0) {
+            const float rho = __fsqrt_rn(sq(ex + CE2E_HALF) + sq(ey + CE2E_HALF));
+            ddx = -(ex + CE2E_HALF) / rho; ddy = -(ey + CE2E_HALF) / rho;
+            if (ey < -CE2E_HALF) { ddx = -1.0f; ddy = 0.0f; }
+            if (ex < -CE2E_HALF) { ddx = 0.0f; ddy = -1.0f; }
+        } else if (task == 1) {
+            ddx = -1.0f;
+        } else {
+            const float rho = __fsqrt_rn(sq(ex - CE2E_HALF) + sq(ey + CE2E_HALF));
+            ddx = (ex - CE2E_HALF) / rho; ddy = (ey + CE2E_HALF) / rho;
+            if (ey < -CE2E_HALF) { ddx = -1.0f; ddy = 0.0f; }
+            if (ex > CE2E_HALF) { ddx = 0.0f; ddy = 1.0f; }
+        }
+        (void)w;
+        g_n[3] += gn[6] * ddx;
+        g_n[4] += gn[6] * ddy;
+        g_n[5] += gn[7];
+        g_n[0] += gn[8];
+        for (int k = 0; k < n_future; ++k) {                             // (fx - x', fy - y', wrap(phi' - fphi))
+            g_n[3] -= gn[9 + 3 * k];
+            g_n[4] -= gn[10 + 3 * k];
+            g_n[5] += gn[11 + 3 * k];
+        }
+    }
+    if (!(vx_raw >= 0.0f && vx_raw <= 35.0f)) g_n[0] = 0.0f;            // clip_by_value (DM:390)
+    // ---- back through f_xu (DM:73-81)
+    {
+        const float tau = K.tau;
+        // vx' = vx + tau (a_x + vy r)
+        gvx += g_n[0]; gvy += g_n[0] * tau * r; gr += g_n[0] * tau * vy; gax += g_n[0] * tau;
+        // vy' = N1 / D1
+        const float D1 = K.m * vx - K.Dv, vy1 = nxt[1];
+        const float k1 = g_n[1] / D1;
+        gvx += k1 * ((K.m * vy - K.tauCf * steer - 2.0f * K.taum * vx * r) - vy1 * K.m);
+        gvy += k1 * (K.m * vx);
+        gr += k1 * (K.tauK1 - K.taum * vx * vx);
+        gsteer += k1 * (-K.tauCf * vx);
+        // r' = N2 / D2
+        const float D2 = K.Dr - K.Iz * vx, r1 = nxt[2];
+        const float k2 = g_n[2] / D2;
+        gvx += k2 * ((-K.Iz * r + K.tauaCf * steer) + r1 * K.Iz);
+        gvy += k2 * (-K.tauK1);
+        gr += k2 * (-K.Iz * vx);
+        gsteer += k2 * (K.tauaCf * vx);
+        // x' = x + tau (vx c - vy s), y' = y + tau (vx s + vy c)
+        gx += g_n[3]; gy += g_n[4];
+        gvx += tau * (g_n[3] * c + g_n[4] * s);
+        gvy += tau * (-g_n[3] * s + g_n[4] * c);
+        gphi += D2R * tau * (g_n[3] * (-vx * s - vy * c) + g_n[4] * (vx * c - vy * s));
+        // phi' = phi + tau r 180/pi
+        gphi += g_n[5];
+        gr += g_n[5] * tau * (180.0f / CE2E_PI32);
+    }
+    float *go = g_obs + i * ld_go;
+    go[0] = gvx; go[1] = gvy; go[2] = gr; go[3] = gx; go[4] = gy; go[5] = gphi;
+    go[6] = g_dy; go[7] = g_dphi; go[8] = g_dv;
+    for (int k = 9; k < 6 + n_trk; ++k) go[k] = 0.0f;
+    g_act[2 * i] = gsteer * m0;
+    g_act[2 * i + 1] = gax * m1;
+}
+
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 int check_task(int task) {
@@ -1186,6 +1380,27 @@ int ce2e_veh_predict(const float *veh_in, int64_t ld_in, const ce2e_turn_classes
     k_veh_predict<<<blocks_for(B * V, 256), 256, 0, (cudaStream_t)stream>>>(veh_in, ld_in, *turn, V,
                                                                              veh_out, ld_out, B);
     return after_launch("k_veh_predict");
+}
+
+int ce2e_rollout_step_backward(const ce2e_paths *paths, int path_index, const int32_t *ref_idx,
+                               const float *obs_in, int64_t ld_in, const float *act_norm, int V_in,
+                               int n_future, const float *g_next, int64_t ld_gnext, const float *g_out5,
+                               float *g_obs, int64_t ld_gobs, float *g_act, int64_t B, void *stream) {
+    int rc;
+    if ((rc = check_batch(B))) return rc;
+    if (B == 0) return CE2E_OK;
+    if (!paths || !obs_in || !act_norm || !g_next || !g_out5 || !g_obs || !g_act)
+        return fail(CE2E_ERR_NULL, "NULL argument");
+    const int n_cols = 6 + 3 * (n_future + 1);
+    if (V_in < 0 || V_in > CE2E_MAX_VEH || n_future < 0 || ld_in < n_cols + 4 * V_in || ld_gnext < n_cols ||
+        ld_gobs < n_cols)
+        return fail(CE2E_ERR_SHAPE, "bad V / n_future / ld");
+    if (!ref_idx && (path_index < 0 || path_index >= paths->n_paths))
+        return fail(CE2E_ERR_PATH, "path_index %d outside [0, %d)", path_index, paths->n_paths);
+    k_model_step_bwd<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
+        make_view(paths), make_grid_view(paths), make_dyn_consts(1.0 / 10.0), paths->task, path_index, ref_idx,
+        obs_in, ld_in, act_norm, V_in, n_future, g_next, ld_gnext, g_out5, g_obs, ld_gobs, g_act, B);
+    return after_launch("k_model_step_bwd");
 }
 
 int ce2e_ss(const float *obs, int64_t ld, const float *next_obs, int64_t ld_next, int V,

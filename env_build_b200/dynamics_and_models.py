@@ -61,9 +61,9 @@ def to_device(x, dtype=torch.float32):
     """NumPy / list / torch (any device) -> CUDA tensor of `dtype` (no copy if already there)."""
     if isinstance(x, torch.Tensor):
         t = _raw(x)
-        if t.is_cuda and t.dtype == dtype and not t.requires_grad:
+        if t.is_cuda and t.dtype == dtype:
             return t
-        return t.detach().to(device=_device(), dtype=dtype)
+        return t.to(device=_device(), dtype=dtype)
     return torch.as_tensor(np.asarray(x), device=_device()).to(dtype)
 
 
@@ -425,6 +425,11 @@ class EnvironmentModel(object):  # all tensors
         if V_out > V_in:
             raise ValueError('observations hold %d vehicles but the mode list has %d' % (V_in, V_out))
         path_index, ref = self._path_args(B)
+        if act.requires_grad or obs.requires_grad:              # differentiable step (autograd.py)
+            from .autograd import RolloutStep
+            nxt, out5, scaled = RolloutStep.apply(obs, act, self, path_index, ref, V_in, V_out)
+            self.actions, self._obs, self.last_out5 = scaled, nxt, out5
+            return (nxt,) + tuple(out5.unbind(0))
         dev = obs.device
         nxt = padded_rows(B, veh_off + 4 * V_out, veh_off, dev)
         out5 = torch.empty((5, B), dtype=torch.float32, device=dev)

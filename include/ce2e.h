@@ -180,6 +180,19 @@ int ce2e_rollout_step(const ce2e_paths *paths, int path_index, const int32_t *re
                       float *obs_out, int64_t ld_out, float *out5, float *act_scaled_out,
                       int64_t B, void *stream);
 
+/* Vector-Jacobian product of EnvironmentModel.rollout_out (DM:118-126), i.e. what TensorFlow's
+ * autodiff gives the reference's model-based trainer: vehicle columns are constants
+ * (tf.stop_gradient, DM:195 / 331 / 402), the closest-waypoint index is an integer (tf.argmin,
+ * DM:714), tf.where / tf.clip_by_value pass the selected branch.  obs_in / act_norm / ref_idx /
+ * path_index: the inputs of the forward ce2e_rollout_step.  g_next [B, 6+3(n+1)] (ld_gnext): upstream
+ * gradient w.r.t. the next ego + tracking columns; g_out5 [5,B]: w.r.t. rewards, punish_term_for_
+ * training, real_punish_term, veh2veh4real, veh2road4real.  Outputs: g_obs [B, 6+3(n+1)] (ld_gobs):
+ * gradient w.r.t. the ego + tracking columns of obs_in; g_act [B,2]: w.r.t. the normalised actions. */
+int ce2e_rollout_step_backward(const ce2e_paths *paths, int path_index, const int32_t *ref_idx,
+                               const float *obs_in, int64_t ld_in, const float *act_norm, int V_in,
+                               int n_future, const float *g_next, int64_t ld_gnext, const float *g_out5,
+                               float *g_obs, int64_t ld_gobs, float *g_act, int64_t B, void *stream);
+
 /* EnvironmentModel.ss(obses, actions, lam) (DM:134-184): discrete barrier penalty.
  * obs/next_obs [B,D] rows with V vehicles each (next_obs from ce2e_rollout_step or
  * compute_next_obses); out [B].                                                           */

@@ -1,0 +1,107 @@
+"""Backward of EnvironmentModel.rollout_out (ce2e_rollout_step_backward through
+env_build_b200/autograd.py) against torch.autograd on the float64 restatement in
+oracle/torch_model.py (the same op graph TensorFlow differentiates in the reference).  Needs a GPU.
+Tolerance: gradients are fp32 on the device and float64 in the oracle -> allclose(rtol=2e-3,
+atol=2e-3); rows whose closest waypoint is a near-tie are excluded (different reference point)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TASKS
+from oracle import crossroad_oracle as orc
+from oracle import torch_model as tm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dm():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from env_build_b200 import _lib
+    if _lib.needs_build():
+        _lib.build()
+    from env_build_b200 import dynamics_and_models
+    return dynamics_and_models
+
+
+def _weights(rng, B, D9):
+    return rng.normal(0, 1, (B, D9)), rng.normal(0, 1, (5, B))
+
+
+def _close(a, b, what):
+    bad = ~np.isclose(a, b, rtol=2e-3, atol=2e-3)
+    assert bad.mean() < 2e-3, (what, int(bad.sum()), a[bad][:5], b[bad][:5])
+
+
+@pytest.mark.parametrize('task', TASKS)
+@pytest.mark.parametrize('steps', [1, 3])
+def test_rollout_gradients(dm, task, steps):
+    from env_build_b200 import synthetic as syn
+    rng = np.random.default_rng(20210315 + steps)
+    B, V = 1500, orc.VEH_NUM[task]
+    model = dm.EnvironmentModel(task, mode='training')
+    paths = model.ref_path.path_list
+    ref = syn.make_ref_indexes(rng, B, out_of_range_frac=0.03)
+    obs = syn.make_obs(rng, B, task, V, paths, ref)
+    tape = syn.make_actions(rng, steps, B)
+    w_obs, w_out = _weights(rng, B, 9)
+
+    # device: leaf tensors on the GPU, loss = sum_t <w_out, out5_t> + <w_obs, next_obs_T[:, :9]>
+    d_obs = torch.tensor(obs, device='cuda', requires_grad=True)
+    d_act = [torch.tensor(tape[t], device='cuda', requires_grad=True) for t in range(steps)]
+    model.reset(d_obs, ref)
+    loss = 0.
+    for t in range(steps):
+        res = model.rollout_out(d_act[t])
+        loss = loss + (torch.stack(res[1:]) * torch.tensor(w_out, device='cuda', dtype=torch.float32)).sum()
+    loss = loss + (res[0][:, :9] * torch.tensor(w_obs, device='cuda', dtype=torch.float32)).sum()
+    loss.backward()
+
+    # oracle: float64 autograd on the CPU
+    o_obs = torch.tensor(obs, dtype=torch.float64, requires_grad=True)
+    o_act = [torch.tensor(tape[t], dtype=torch.float64, requires_grad=True) for t in range(steps)]
+    cur, oloss = o_obs, 0.
+    margin = np.full(B, np.inf)
+    om = orc.EnvironmentModel(task, mode='training', path_list=paths)
+    om.reset(obs, ref)
+    for t in range(steps):
+        _, mg = om.compute_next_obses(om.obses, orc.action_transformation(tape[t]), return_margin=True)
+        margin = np.minimum(margin, mg)
+        om.rollout_out(tape[t])
+        res_o = tm.rollout_out(cur, o_act[t], task, ref, paths, orc.VEHICLE_MODE_LIST[task])
+        oloss = oloss + (torch.stack(res_o[1:]) * torch.tensor(w_out)).sum()
+        cur = res_o[0]
+    oloss = oloss + (cur[:, :9] * torch.tensor(w_obs)).sum()
+    oloss.backward()
+
+    ok = margin > 1e-3
+    assert ok.mean() > 0.9
+    assert abs(float(loss.detach()) - float(oloss.detach())) <= 1e-3 * abs(float(oloss.detach())) + 1e-2 * steps or not ok.all()
+    for t in range(steps):
+        _close(d_act[t].grad.cpu().numpy()[ok], o_act[t].grad.numpy()[ok], 'd loss / d action[%d]' % t)
+    g, go = d_obs.grad.cpu().numpy(), o_obs.grad.numpy()
+    _close(g[ok][:, :9], go[ok][:, :9], 'd loss / d obs (ego + tracking)')
+    assert np.abs(g[:, 9:]).max() == 0 and np.abs(go[:, 9:]).max() == 0        # stop_gradient on vehicles
+    # clipped actions carry no gradient (tf.clip_by_value, DM:129)
+    clipped = np.abs(tape[-1]) > 1.05
+    assert np.abs(d_act[-1].grad.cpu().numpy()[clipped]).max(initial=0.0) == 0
+
+
+def test_no_grad_path_unchanged(dm):
+    """Without requires_grad the call takes the plain path and returns the same numbers."""
+    from env_build_b200 import synthetic as syn
+    rng = np.random.default_rng(4)
+    task, B = 'left', 777
+    model = dm.EnvironmentModel(task, mode='training')
+    ref = syn.make_ref_indexes(rng, B)
+    obs = syn.make_obs(rng, B, task, 8, model.ref_path.path_list, ref)
+    act = syn.make_actions(rng, 1, B)[0]
+    model.reset(obs, ref)
+    plain = [r.numpy() for r in model.rollout_out(act)]
+    model.reset(obs, ref)
+    a = torch.tensor(act, device='cuda', requires_grad=True)
+    diff = model.rollout_out(a)
+    for p, d in zip(plain, diff):
+        assert np.array_equal(p.view(np.int32), d.detach().cpu().numpy().view(np.int32))
+    assert diff[1].requires_grad and diff[0].requires_grad
