@@ -292,7 +292,7 @@ def run_ours(args):
         out_all.record_stream(side)
         final.record_stream(side)
 
-    ke = max(3, min(K, 10))
+    ke = max(3, min(K, 20))
     ms_e = timed(e2e_step, 3, ke, after=lambda: torch.cuda.current_stream().wait_stream(side))
     e2e_value = world * B * H * ke / (ms_e / 1e3)
     h2d = obs.nbytes + ref.nbytes + tape.nbytes

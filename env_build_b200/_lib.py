@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 INCLUDE = os.path.join(os.path.dirname(_HERE), 'include')
-LIB_PATH = os.path.join(CSRC, 'libce2e.so')
+LIB_PATH = os.environ.get('CE2E_LIB') or os.path.join(CSRC, 'libce2e.so')   # CE2E_LIB: A/B-test another build
 
 MAX_PATHS = 4
 MAX_VEH = 256

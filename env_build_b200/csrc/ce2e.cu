@@ -206,9 +206,11 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
-// Hinge-queue accesses.  No "memory" clobber on purpose: the queue is touched only through these
-// two (volatile asm statements keep their mutual order), and a clobber would pin every vehicle
-// load / store of the chunk buffer around them and serialise the two interleaved vehicles.
+// Block-wide named barrier, NON-aligned form: the warps of a block reach it from two different
+// places (inside their first tile, or after the tile loop when they own no tile).
+__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
+    asm volatile("barrier.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v));
 }
@@ -247,25 +249,18 @@ __device__ __forceinline__ float4 vehicle_step(float4 v, const Circles &ec, int 
     return NEXT ? veh_predict_one(v, th, vs, vc, tc) : v;
 }
 
-// The nearest-waypoint candidate cell of (x, y) on path p: lo | hi << 16 from the grid, or the whole
-// path (0 | (N-1) << 16) when the point is off the grid / not finite.  The load is issued here; the
-// fused step consumes it only after the vehicle phase, which hides its latency.
-__device__ __forceinline__ uint32_t candidate_cell(const GridView &gv, int p, int n, float x, float y) {
-    uint32_t c = (uint32_t)(n - 1) << 16;
-    const float tx = (x - gv.x0[p]) * gv.inv_h, ty = (y - gv.y0[p]) * gv.inv_h;
-    if (tx >= 0.0f && ty >= 0.0f && tx < (float)gv.nx[p] && ty < (float)gv.ny[p])
-        c = __ldg(gv.cells + gv.off[p] + (int)ty * gv.nx[p] + (int)tx);
-    return c;
-}
-// [lo, hi] widened to even bounds [k0, k1)
-__device__ __forceinline__ void cell_range(uint32_t c, int &k0, int &k1) {
-    k0 = (int)(c & 0xffffu) & ~1;
-    k1 = ((int)(c >> 16) + 2) & ~1;
-}
+// The nearest-waypoint candidate range of (x, y) on path p: the grid cell's [lo, hi] widened to
+// even bounds, or everything when the point is off the grid / not finite.
 __device__ __forceinline__ void candidate_range(const GridView &gv, int p, int n_even, float x, float y,
                                                 int &k0, int &k1) {
-    (void)n_even;
-    cell_range(candidate_cell(gv, p, n_even, x, y), k0, k1);
+    k0 = 0;
+    k1 = n_even;
+    const float tx = (x - gv.x0[p]) * gv.inv_h, ty = (y - gv.y0[p]) * gv.inv_h;
+    if (tx >= 0.0f && ty >= 0.0f && tx < (float)gv.nx[p] && ty < (float)gv.ny[p]) {
+        const uint32_t c = __ldg(gv.cells + gv.off[p] + (int)ty * gv.nx[p] + (int)tx);
+        k0 = (int)(c & 0xffffu) & ~1;
+        k1 = ((int)(c >> 16) + 2) & ~1;
+    }
 }
 
 // Work decomposition (DESIGN.md "k_model_step"): two lanes per observation row.
@@ -295,20 +290,15 @@ k_model_step(const __grid_constant__ StepParams P) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool vec_in = P.flags & F_VEC_IN, vec_out = P.flags & F_VEC_OUT;
     bool tables_pending = false;
-    __shared__ __align__(8) unsigned long long s_table_bar;
-    const unsigned table_bar = (unsigned)__cvta_generic_to_shared(&s_table_bar);
     if (NEXT) {
         // path tables -> shared memory with 8 B async copies; they are static, so this may run
-        // before the previous launch has finished (programmatic dependent launch).  Every thread
-        // makes an mbarrier track its copies; a warp waits on it only right before its first
-        // waypoint scan (after the vehicle phase), by when the tables have long landed.
-        if (tid == 0) asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"(table_bar), "r"(STEP_THREADS) : "memory");
-        __syncthreads();
+        // before the previous launch has finished (programmatic dependent launch) and is only
+        // waited for right before the first waypoint scan
         const int tot = P.pv.n_paths * P.pv.stride;           // stride is even: tot * 4 B is a multiple of 8
         const unsigned sx = (unsigned)__cvta_generic_to_shared(s_xy), sp = (unsigned)__cvta_generic_to_shared(s_phi);
         for (int i = tid; i < tot; i += STEP_THREADS) cp_async8(sx + 8u * i, P.pv.xy + i);
         for (int i = tid; i < tot / 2; i += STEP_THREADS) cp_async8(sp + 8u * i, P.pv.phi + 2 * i);
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];\n" ::"r"(table_bar) : "memory");
+        cp_async_commit();
         tables_pending = true;
     }
     // everything below reads what the previous launch of a rollout wrote
@@ -390,6 +380,12 @@ k_model_step(const __grid_constant__ StepParams P) {
         float s, c;
         sincos_cw(phi, s, c);
         const Circles ec = circle_centres(x, y, s, c);
+        if (tables_pending) {                 // first tile of this warp: the path tables must have
+            cp_async_wait<1>();               // landed (the vehicle chunk staged above may still fly)
+            tables_pending = false;
+            named_barrier_sync(1, STEP_THREADS);
+        }
+
         float rewards = 0.f, v2r_tr = 0.f, v2r_re = 0.f;
         if (REW && (h == 0 || !NEXT)) {                                  // reward lane
             const float punish_steer = -sq(steer);                       // DM:198-207
@@ -411,13 +407,8 @@ k_model_step(const __grid_constant__ StepParams P) {
                 d[9 * B] = 0.05f * devi_v; d[10 * B] = 0.8f * devi_y; d[11 * B] = 30.0f * devi_phi;
             }
         }
-        // dynamics lane, early part: integrate f_xu and issue the candidate-cell load; the scan and
-        // the tracking error run after the vehicle phase, which hides the load's latency
-        float nxt[6];
-        int p = 0;
-        bool p_ok = false;
-        uint32_t cell = 0;
-        if (NEXT && (h == 1 || !REW)) {
+        if (NEXT && (h == 1 || !REW)) {                                  // dynamics lane
+            float nxt[6];
             f_xu_next(P.dyn, vx, vy, r, x, y, phi, s, c, steer, a_x, nxt);
             if (P.flags & F_GYM_EGO) {                                   // E2E:281-282
                 nxt[0] = (nxt[0] >= 0.0f) ? nxt[0] : 0.0f;
@@ -425,13 +416,43 @@ k_model_step(const __grid_constant__ StepParams P) {
             } else {
                 nxt[0] = fminf(fmaxf(nxt[0], 0.0f), 35.0f);              // ego_predict, DM:390
             }
-            p = P.ref_idx ? P.ref_idx[rr] : P.path_index;
-            p_ok = (p >= 0) && (p < P.pv.n_paths);
+            int p = P.ref_idx ? P.ref_idx[rr] : P.path_index;
+            const bool p_ok = (p >= 0) && (p < P.pv.n_paths);
             p = p_ok ? p : 0;
-            cell = candidate_cell(P.gv, p, (P.pv.N[p] + 1) & ~1, nxt[3], nxt[4]);
-            if (valid && h == 1 && P.act_scaled_out) {
-                P.act_scaled_out[2 * row] = steer;
-                P.act_scaled_out[2 * row + 1] = a_x;
+            const float2 *t_xy = s_xy + (size_t)p * P.pv.stride;
+            int k0, k1;
+            candidate_range(P.gv, p, (P.pv.N[p] + 1) & ~1, nxt[3], nxt[4], k0, k1);
+            float best;
+            int bi;
+            scan_min(t_xy, k0, k1, nxt[3], nxt[4], best, bi);
+            if (valid && h == 1) {
+                float *q = P.obs_out + row * P.ld_out;
+                float t9[3];
+                if (p_ok) {
+                    tracking_from_index(t_xy, s_phi + (size_t)p * P.pv.stride, P.pv.L[p],
+                                        P.pv.tail[p], P.task, bi, nxt[3], nxt[4], nxt[5], nxt[0],
+                                        0, t9);
+                    if (P.n_future > 0)
+                        tracking_from_index(t_xy, s_phi + (size_t)p * P.pv.stride, P.pv.L[p],
+                                            P.pv.tail[p], P.task, bi, nxt[3], nxt[4], nxt[5], nxt[0],
+                                            P.n_future, q + 6);
+                } else {
+                    t9[0] = t9[1] = t9[2] = 0.0f;
+                    for (int i = 3; i < n_trk; ++i) q[6 + i] = 0.0f;     // DM:342-343
+                }
+                if (vec_out && veh_off == 9) {
+                    q[0] = nxt[0];
+                    *reinterpret_cast<float4 *>(q + 1) = make_float4(nxt[1], nxt[2], nxt[3], nxt[4]);
+                    *reinterpret_cast<float4 *>(q + 5) = make_float4(nxt[5], t9[0], t9[1], t9[2]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) q[i] = nxt[i];
+                    q[6] = t9[0]; q[7] = t9[1]; q[8] = t9[2];
+                }
+                if (P.act_scaled_out) {
+                    P.act_scaled_out[2 * row] = steer;
+                    P.act_scaled_out[2 * row + 1] = a_x;
+                }
             }
         }
 
@@ -503,51 +524,6 @@ k_model_step(const __grid_constant__ StepParams P) {
         }
         cp_async_wait<0>();
 
-        if (tables_pending) {                 // first tile of this warp: the path tables (staged
-            tables_pending = false;           // asynchronously at kernel start) must have landed
-            asm volatile(
-                "{\n"
-                ".reg .pred p;\n"
-                "TABLE_WAIT:\n"
-                "mbarrier.try_wait.parity.shared.b64 p, [%0], 0;\n"
-                "@!p bra TABLE_WAIT;\n"
-                "}\n" ::"r"(table_bar) : "memory");
-        }
-        // dynamics lane, late part: closest waypoint in the candidate range, tracking error, stores
-        if (NEXT && (h == 1 || !REW)) {
-            const float2 *t_xy = s_xy + (size_t)p * P.pv.stride;
-            int k0, k1;
-            cell_range(cell, k0, k1);
-            float best;
-            int bi;
-            scan_min(t_xy, k0, k1, nxt[3], nxt[4], best, bi);
-            if (valid && h == 1) {
-                float *q = P.obs_out + row * P.ld_out;
-                float t9[3];
-                if (p_ok) {
-                    tracking_from_index(t_xy, s_phi + (size_t)p * P.pv.stride, P.pv.L[p],
-                                        P.pv.tail[p], P.task, bi, nxt[3], nxt[4], nxt[5], nxt[0],
-                                        0, t9);
-                    if (P.n_future > 0)
-                        tracking_from_index(t_xy, s_phi + (size_t)p * P.pv.stride, P.pv.L[p],
-                                            P.pv.tail[p], P.task, bi, nxt[3], nxt[4], nxt[5], nxt[0],
-                                            P.n_future, q + 6);
-                } else {
-                    t9[0] = t9[1] = t9[2] = 0.0f;
-                    for (int i = 3; i < n_trk; ++i) q[6 + i] = 0.0f;     // DM:342-343
-                }
-                if (vec_out && veh_off == 9) {
-                    q[0] = nxt[0];
-                    *reinterpret_cast<float4 *>(q + 1) = make_float4(nxt[1], nxt[2], nxt[3], nxt[4]);
-                    *reinterpret_cast<float4 *>(q + 5) = make_float4(nxt[5], t9[0], t9[1], t9[2]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) q[i] = nxt[i];
-                    q[6] = t9[0]; q[7] = t9[1]; q[8] = t9[2];
-                }
-            }
-        }
-
         if (REW) {
             flush();
             // (first half) + (second half); the reward lane (h = 0, or both when !NEXT) writes
@@ -569,7 +545,10 @@ k_model_step(const __grid_constant__ StepParams P) {
             }
         }
     }
-    cp_async_wait<0>();                       // a warp without tiles must not exit with copies in flight
+    if (tables_pending) {                     // a warp without tiles still owes the block its arrival
+        cp_async_wait<0>();
+        named_barrier_sync(1, STEP_THREADS);
+    }
 }
 
 GridView make_grid_view(const ce2e_paths *p) {
