@@ -1063,6 +1063,108 @@ __global__ void k_model_step_bwd(const __grid_constant__ PathView pv, const __gr
     g_act[2 * i + 1] = gax * m1;
 }
 
+// ------------------------------------------------------------------------------------------
+// interested-vehicle selection
+// ------------------------------------------------------------------------------------------
+// CrossroadEnd2end._construct_veh_vector_short (E2E:340-464) for B scenes: from the N vehicles
+// around each ego keep, per route class of VEHICLE_MODE_DICT[task] (EU:21-23), the vehicles that
+// pass the class's range filter (E2E:393-411), order them by the class's sort key (E2E:414-428,
+// Python's stable sort: equal keys keep their list order) and emit the first `num`, padding with
+// the class's far-away fill vehicle (E2E:440-447).  One thread per (scene, class).
+// Route classes (the order of the reference's local lists, E2E:354): 0 dl, 1 du, 2 dr, 3 rd, 4 rl,
+// 5 ru, 6 ur, 7 ud, 8 ul, 9 lu, 10 lr, 11 ld; anything else is ignored.
+struct SelectSpec {
+    int n_modes;
+    int cls[5];        // route class of each selected mode, in VEHICLE_MODE_DICT[task] order
+    int num[5];        // vehicles kept per mode
+    int slot0[5];      // first output slot of the mode
+};
+
+__device__ __forceinline__ bool veh_in_range(int cls, int task, float x, float y, float ex, float ey) {
+    switch (cls) {
+        case 0: return x > -35.0f && y > ey - 2.0f;                                          // dl
+        case 1: return ey - 2.0f < y && y < 35.0f && x < ex + 5.0f;                          // du
+        case 2: return x < 35.0f && y > ey;                                                  // dr
+        case 5: return x < 35.0f && y < 35.0f;                                               // ru
+        case 6: return task == 1 ? (x < ex + 7.0f && ey < y && y < 35.0f)                    // ur
+                                 : (task == 2 ? (x < 35.0f && y < 25.0f) : true);
+        case 7: return fmaxf(ey - 2.0f, -25.0f) < y && y < 25.0f && ex > x;                  // ud
+        case 8: return -35.0f < x && x < ex && y < 25.0f;                                    // ul
+        case 10: return -35.0f < x && x < 35.0f;                                             // lr
+        default: return true;
+    }
+}
+// ascending lexicographic key (k1, k2) equivalent to the reference's sorted(...) call
+__device__ __forceinline__ void veh_sort_key(int cls, int task, float x, float y, float &k1, float &k2) {
+    switch (cls) {
+        case 0: k1 = y; k2 = -x; break;                       // (y, -x)
+        case 2: k1 = y; k2 = x; break;                        // (y, x)
+        case 5: k1 = x; k2 = -y; break;                       // reverse of (-x, y)
+        case 6: k1 = y; k2 = (task == 2) ? -x : 0.0f; break;  // straight: y; right: reverse of (-y, x)
+        case 8: k1 = y; k2 = x; break;                        // reverse of (-y, -x)
+        case 10: k1 = -x; k2 = 0.0f; break;                   // -x
+        default: k1 = y; k2 = 0.0f; break;                    // du, ud: y
+    }
+}
+__device__ __forceinline__ float4 veh_fill_value(int cls) {
+    switch (cls) {                                            // mode2fillvalue, E2E:440-447
+        case 0: return make_float4(CE2E_LW / 2.0f, -55.0f, 0.0f, 90.0f);
+        case 1: return make_float4(CE2E_LW * 1.5f, -55.0f, 0.0f, 90.0f);
+        case 2: return make_float4(CE2E_LW * 2.5f, -55.0f, 0.0f, 90.0f);
+        case 5: return make_float4(40.0f, CE2E_LW * 2.5f, 0.0f, 180.0f);
+        case 6: return make_float4(-CE2E_LW / 2.0f, 45.0f, 0.0f, -90.0f);
+        case 7: return make_float4(-CE2E_LW * 1.5f, 45.0f, 0.0f, -90.0f);
+        case 8: return make_float4(-CE2E_LW * 2.5f, 45.0f, 0.0f, -90.0f);
+        default: return make_float4(-45.0f, -CE2E_LW * 1.5f, 0.0f, 0.0f);       // lr
+    }
+}
+
+__global__ void k_select_vehicles(const __grid_constant__ SelectSpec spec, int task,
+                                  const float *__restrict__ veh_all, const int8_t *__restrict__ route_class,
+                                  int N, const float *__restrict__ ego_xy, int v_light,
+                                  const int8_t *__restrict__ virtual_red, float *__restrict__ out, int64_t ld,
+                                  int64_t B) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * spec.n_modes) return;
+    const int64_t i = t / spec.n_modes;
+    const int m = (int)(t - i * spec.n_modes);
+    const int cls = spec.cls[m], num = spec.num[m];
+    const float ex = ego_xy[2 * i], ey = ego_xy[2 * i + 1];
+    // best two candidates by (k1, k2, list index)
+    float b1[2] = {CUDART_INF_F, CUDART_INF_F}, b2[2] = {CUDART_INF_F, CUDART_INF_F};
+    float4 bv[2];
+    int nb = 0;
+    bv[0] = bv[1] = veh_fill_value(cls);
+    auto consider = [&](float4 v) {
+        if (!veh_in_range(cls, task, v.x, v.y, ex, ey)) return;
+        float k1, k2;
+        veh_sort_key(cls, task, v.x, v.y, k1, k2);
+        // strict "<": an equal key never displaces an earlier list entry (stable sort)
+        const bool lt0 = nb < 1 || k1 < b1[0] || (k1 == b1[0] && k2 < b2[0]);
+        const bool lt1 = nb < 2 || k1 < b1[1] || (k1 == b1[1] && k2 < b2[1]);
+        if (lt0) {
+            b1[1] = b1[0]; b2[1] = b2[0]; bv[1] = bv[0];
+            b1[0] = k1; b2[0] = k2; bv[0] = v;
+        } else if (lt1) {
+            b1[1] = k1; b2[1] = k2; bv[1] = v;
+        }
+        nb = min(nb + 1, 2);
+    };
+    const float *va = veh_all + i * (int64_t)N * 4;
+    const int8_t *rc = route_class + i * (int64_t)N;
+    for (int j = 0; j < N; ++j)
+        if (rc[j] == cls) consider(make_float4(va[4 * j], va[4 * j + 1], va[4 * j + 2], va[4 * j + 3]));
+    // virtual stopped vehicles at the stop line under a red light (E2E:386-390), appended last
+    if (task != 2 && (cls == 0 || cls == 1) && ey < -CE2E_HALF && (v_light != 0 || (virtual_red && virtual_red[i])))
+        consider(make_float4(cls == 0 ? CE2E_LW / 2.0f : CE2E_LW * 1.5f, -CE2E_HALF + 2.5f, 0.0f, 90.0f));
+    const float4 fill = veh_fill_value(cls);
+    float *o = out + i * ld + 4 * spec.slot0[m];
+    for (int k = 0; k < num; ++k) {
+        const float4 v = (k < nb) ? bv[k] : fill;
+        o[4 * k] = v.x; o[4 * k + 1] = v.y; o[4 * k + 2] = v.z; o[4 * k + 3] = v.w;
+    }
+}
+
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 int check_task(int task) {
@@ -1401,6 +1503,34 @@ int ce2e_rollout_step_backward(const ce2e_paths *paths, int path_index, const in
         make_view(paths), make_grid_view(paths), make_dyn_consts(1.0 / 10.0), paths->task, path_index, ref_idx,
         obs_in, ld_in, act_norm, V_in, n_future, g_next, ld_gnext, g_out5, g_obs, ld_gobs, g_act, B);
     return after_launch("k_model_step_bwd");
+}
+
+int ce2e_select_vehicles(int task, const float *veh_all, const int8_t *route_class, int N,
+                         const float *ego_xy, int v_light, const int8_t *virtual_red, float *out,
+                         int64_t ld_out, int64_t B, void *stream) {
+    int rc;
+    if ((rc = check_batch(B))) return rc;
+    if ((rc = check_task(task))) return rc;
+    if (B == 0) return CE2E_OK;
+    if (!ego_xy || !out || (N > 0 && (!veh_all || !route_class))) return fail(CE2E_ERR_NULL, "NULL argument");
+    SelectSpec spec;
+    memset(&spec, 0, sizeof(spec));
+    // VEHICLE_MODE_DICT (EU:21-23)
+    static const int cls_left[4] = {0, 1, 7, 8}, num_left[4] = {2, 2, 2, 2};
+    static const int cls_straight[5] = {0, 1, 7, 5, 6}, num_straight[5] = {1, 2, 2, 2, 2};
+    static const int cls_right[3] = {2, 6, 10}, num_right[3] = {1, 2, 2};
+    const int *cls = task == 0 ? cls_left : task == 1 ? cls_straight : cls_right;
+    const int *num = task == 0 ? num_left : task == 1 ? num_straight : num_right;
+    spec.n_modes = task == 0 ? 4 : task == 1 ? 5 : 3;
+    int slot = 0;
+    for (int m = 0; m < spec.n_modes; ++m) {
+        spec.cls[m] = cls[m]; spec.num[m] = num[m]; spec.slot0[m] = slot;
+        slot += num[m];
+    }
+    if (N < 0 || ld_out < 4 * slot) return fail(CE2E_ERR_SHAPE, "bad N / ld_out (need %d columns)", 4 * slot);
+    k_select_vehicles<<<blocks_for(B * spec.n_modes, 128), 128, 0, (cudaStream_t)stream>>>(
+        spec, task, veh_all, route_class, N, ego_xy, v_light, virtual_red, out, ld_out, B);
+    return after_launch("k_select_vehicles");
 }
 
 int ce2e_ss(const float *obs, int64_t ld, const float *next_obs, int64_t ld_next, int V,

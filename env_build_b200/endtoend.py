@@ -28,6 +28,26 @@ DONE_TYPES = ('not_done_yet', 'collision', 'break_road_constrain', 'deviate_too_
 _RESET_SPAN = dict(left=900 + 500, straight=1200 + 500, right=420 + 500)
 
 
+# route classes of the interested-vehicle selection, in the order of the reference's local lists (E2E:354)
+ROUTE_CLASSES = ('dl', 'du', 'dr', 'rd', 'rl', 'ru', 'ur', 'ud', 'ul', 'lu', 'lr', 'ld')
+# arm names seen from each ego exit (E2E:346-349): d(own) r(ight) u(p) l(eft) -> SUMO edge number
+_ARMS = dict(D='1234', R='2341', U='3412', L='4123')
+
+
+def route_class(route, exit_='D'):
+    """Index into ROUTE_CLASSES of a SUMO route (start_edge, end_edge) such as ('1o', '4i') as seen by an
+    ego entering from `exit_` (E2E:355-382); -1 for anything else (e.g. the ego's own padding)."""
+    try:
+        start, end = route[0], route[1]
+        arms = _ARMS[exit_]
+        a, b = 'drul'[arms.index(start[0])], 'drul'[arms.index(end[0])]
+        if start[1] != 'o' or end[1] != 'i' or a == b:
+            return -1
+        return ROUTE_CLASSES.index(a + b)
+    except (ValueError, IndexError, TypeError, KeyError):
+        return -1
+
+
 class Box(object):
     """Minimal stand-in for gym.spaces.Box (gym is not a dependency of this package)."""
 
@@ -205,6 +225,33 @@ class CrossroadEnd2end(object):
             code = int(done.item())
             return DONE_TYPES[code], int(code != 0)
         return _wrap(done), _wrap(done != 0)
+
+    # -- interested-vehicle selection (E2E:340-464) ------------------------------------------------
+    def construct_veh_vectors(self, veh_all, route_classes, ego_xy, virtual_red=None):
+        """Batched _construct_veh_vector_short: veh_all [B,N,4] (x, y, v, phi), route_classes [B,N]
+        (indexes into ROUTE_CLASSES, see route_class()), ego_xy [B,2] -> [B, 4*VEH_NUM[task]]."""
+        veh = to_device(veh_all).contiguous()
+        cls = to_device(route_classes, torch.int8).contiguous()
+        ego = to_device(ego_xy).contiguous()
+        B, N = veh.shape[0], veh.shape[1]
+        if veh.dim() != 3 or veh.shape[2] != 4 or tuple(cls.shape) != (B, N) or tuple(ego.shape) != (B, 2):
+            raise ValueError('expected veh_all [B,N,4], route_classes [B,N], ego_xy [B,2]')
+        vr = None if virtual_red is None else to_device(virtual_red, torch.int8).reshape(B).contiguous()
+        V = VEH_NUM[self.training_task]
+        out = torch.empty((B, 4 * V), dtype=torch.float32, device=veh.device)
+        _lib.check(_lib.load().ce2e_select_vehicles(_lib.TASK_ID[self.training_task], _ptr(veh), _ptr(cls), N, _ptr(ego),
+                                                    int(self.v_light), _ptr(vr), _ptr(out), 4 * V, B, _stream()))
+        return _wrap(out)
+
+    def _construct_veh_vector_short(self, exit_='D'):
+        """E2E:340-464 for one environment whose `all_vehicles` is the reference's list of dicts
+        (x, y, v, phi, route, ...) and whose ego position is taken from the current observation."""
+        vehs = getattr(self, 'all_vehicles', None) or []
+        veh = np.array([[v['x'], v['y'], v['v'], v['phi']] for v in vehs], np.float32).reshape(1, -1, 4)
+        cls = np.array([route_class(v.get('route'), exit_) for v in vehs], np.int8).reshape(1, -1)
+        ego = self.obs.numpy()[:1, 3:5]
+        vr = np.array([1 if getattr(self, 'virtual_red_light_vehicle', False) else 0], np.int8)
+        return self.construct_veh_vectors(veh, cls, ego, vr).numpy()[0]
 
     # -- reference-named numeric helpers (batch-1 callers) ---------------------------------------
     def _ego_dynamics_dict(self):

@@ -193,6 +193,18 @@ int ce2e_rollout_step_backward(const ce2e_paths *paths, int path_index, const in
                                int n_future, const float *g_next, int64_t ld_gnext, const float *g_out5,
                                float *g_obs, int64_t ld_gobs, float *g_act, int64_t B, void *stream);
 
+/* CrossroadEnd2end._construct_veh_vector_short (E2E:340-464) for B scenes: veh_all [B,N,4] =
+ * (x, y, v, phi_deg) of the vehicles around each ego, route_class [B,N] int8 = 0 dl, 1 du, 2 dr,
+ * 3 rd, 4 rl, 5 ru, 6 ur, 7 ud, 8 ul, 9 lu, 10 lr, 11 ld (the lists of E2E:354; other values are
+ * ignored), ego_xy [B,2], v_light as in the reference (0 = green), virtual_red [B] int8 or NULL =
+ * self.virtual_red_light_vehicle (E2E:120-124).  out [B, 4*VEH_NUM[task]] (ld_out): per route
+ * class of VEHICLE_MODE_DICT[task] (EU:21-23) the vehicles passing the range filter (E2E:393-411),
+ * stably sorted by the class's key (E2E:414-428), cut / padded to the class's count with the fill
+ * vehicles of E2E:440-447.                                                                    */
+int ce2e_select_vehicles(int task, const float *veh_all, const int8_t *route_class, int N,
+                         const float *ego_xy, int v_light, const int8_t *virtual_red, float *out,
+                         int64_t ld_out, int64_t B, void *stream);
+
 /* EnvironmentModel.ss(obses, actions, lam) (DM:134-184): discrete barrier penalty.
  * obs/next_obs [B,D] rows with V vehicles each (next_obs from ce2e_rollout_step or
  * compute_next_obses); out [B].                                                           */

@@ -734,3 +734,56 @@ def gym_env_step(obs, actions_norm, task, ref_indexes, path_list, mode_list, num
     next_obs = np.concatenate([nxt, trk, veh], 1).astype(f32)
     code, margin = gym_judge_done(nxt, params, next_obs[:, 6], veh, task, v_light)
     return next_obs, reward, code, margin
+
+
+# ----------------------------------------------------------------------------
+# interested-vehicle selection -- endtoend.py:340-464
+# ----------------------------------------------------------------------------
+ROUTE_CLASSES = ('dl', 'du', 'dr', 'rd', 'rl', 'ru', 'ur', 'ud', 'ul', 'lu', 'lr', 'ld')   # E2E:354
+VEHICLE_MODE_DICT = dict(left=(('dl', 2), ('du', 2), ('ud', 2), ('ul', 2)),
+                         straight=(('dl', 1), ('du', 2), ('ud', 2), ('ru', 2), ('ur', 2)),
+                         right=(('dr', 1), ('ur', 2), ('lr', 2)))                           # EU:21-23
+
+
+def select_interested_vehicles(veh, classes, ego_x, ego_y, task, v_light=0, virtual_red=False):
+    """One scene of CrossroadEnd2end._construct_veh_vector_short (E2E:340-464).  veh [N,4] fp32
+    rows (x, y, v, phi), classes [N] indexes into ROUTE_CLASSES (other values ignored).
+    Returns the [4*VEH_NUM[task]] fp32 vehicle vector.  Pinned against the unmodified reference
+    method by tests/golden/make_golden_env.py (sel_* arrays)."""
+    half, lw, ln = CROSSROAD_SIZE / 2, LANE_WIDTH, LANE_NUMBER
+    ex, ey = f32(ego_x), f32(ego_y)
+    lists = {m: [] for m in ROUTE_CLASSES}
+    for row, c in zip(np.asarray(veh, dtype=f32), classes):
+        if 0 <= c < len(ROUTE_CLASSES):
+            lists[ROUTE_CLASSES[c]].append(tuple(float(t) for t in row))
+    if task != 'right' and ey < -half and (v_light != 0 or virtual_red):                    # E2E:386-390
+        lists['dl'].append((lw / 2, -half + 2.5, 0., 90.))
+        lists['du'].append((lw * 1.5, -half + 2.5, 0., 90.))
+    X, Y = 0, 1
+    keep = dict(                                                                           # E2E:393-411
+        dl=lambda v: v[X] > -half - 10 and v[Y] > ey - 2,
+        du=lambda v: ey - 2 < v[Y] < half + 10 and v[X] < ex + 5,
+        dr=lambda v: v[X] < half + 10 and v[Y] > ey,
+        ru=lambda v: v[X] < half + 10 and v[Y] < half + 10,
+        ur=(lambda v: v[X] < ex + 7 and ey < v[Y] < half + 10) if task == 'straight' else
+           (lambda v: v[X] < half + 10 and v[Y] < half) if task == 'right' else (lambda v: True),
+        ud=lambda v: max(ey - 2, -half) < v[Y] < half and ex > v[X],
+        ul=lambda v: -half - 10 < v[X] < ex and v[Y] < half,
+        lr=lambda v: -half - 10 < v[X] < half + 10)
+    order = dict(                                                                          # E2E:414-428
+        dl=(lambda v: (v[Y], -v[X]), False), du=(lambda v: v[Y], False), dr=(lambda v: (v[Y], v[X]), False),
+        ru=(lambda v: (-v[X], v[Y]), True),
+        ur=(lambda v: v[Y], False) if task == 'straight' else (lambda v: (-v[Y], v[X]), True),
+        ud=(lambda v: v[Y], False), ul=(lambda v: (-v[Y], -v[X]), True), lr=(lambda v: -v[X], False))
+    fill = dict(dl=(lw / 2, -(half + 30), 0, 90), du=(lw * 1.5, -(half + 30), 0, 90),           # E2E:440-447
+                dr=(lw * (ln - 0.5), -(half + 30), 0, 90), ru=(half + 15, lw * (ln - 0.5), 0, 180),
+                ur=(-lw / 2, half + 20, 0, -90), ud=(-lw * 1.5, half + 20, 0, -90),
+                ul=(-lw * (ln - 0.5), half + 20, 0, -90), lr=(-(half + 20), -lw * 1.5, 0, 0))
+    out = []
+    for mode, num in VEHICLE_MODE_DICT[task]:
+        key, rev = order[mode]
+        chosen = sorted([v for v in lists[mode] if keep[mode](v)], key=key, reverse=rev)[:num]
+        chosen += [fill[mode]] * (num - len(chosen))
+        for v in chosen:
+            out.extend(v)
+    return np.array(out, dtype=f32)

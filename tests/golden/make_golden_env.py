@@ -15,6 +15,7 @@ methods read; the methods themselves run unmodified:
   CrossroadEnd2end.compute_reward                       E2E:501-507
   CrossroadEnd2end._judge_done (+ the five predicates)  E2E:200-256
   Traffic.collision_check                               traffic.py:263-295
+  CrossroadEnd2end._construct_veh_vector_short          E2E:340-464
 
 Output: tests/golden/env_<task>.npz (inputs and outputs of those calls, one row per sample).
 """
@@ -111,6 +112,33 @@ def main():
                    predicates=np.array(parts, bool),
                    _doc=np.array('unmodified reference endtoend.py:150-283,501-507 and traffic.py:263-295 on stand-in '
                                  'imports; rows = independent single-env calls'))
+        # ---- _construct_veh_vector_short (E2E:340-464) on random scenes --------------------------
+        classes = ('dl', 'du', 'dr', 'rd', 'rl', 'ru', 'ur', 'ud', 'ul', 'lu', 'lr', 'ld')
+        route = dict(dl=('1o', '4i'), du=('1o', '3i'), dr=('1o', '2i'), rd=('2o', '1i'), rl=('2o', '4i'),
+                     ru=('2o', '3i'), ur=('3o', '2i'), ud=('3o', '1i'), ul=('3o', '4i'), lu=('4o', '3i'),
+                     lr=('4o', '2i'), ld=('4o', '1i'))
+        S, NV = 300, 40
+        sel_veh = np.zeros((S, NV, 4), np.float32)
+        sel_veh[:, :, 0] = np.round(rng.uniform(-45, 45, (S, NV)) * 2) / 2         # half-metre grid: many key ties
+        sel_veh[:, :, 1] = np.round(rng.uniform(-60, 50, (S, NV)) * 2) / 2
+        sel_veh[:, :, 2] = rng.uniform(0, 8, (S, NV))
+        sel_veh[:, :, 3] = rng.choice([0., 90., 180., -90.], (S, NV))
+        sel_cls = rng.integers(-1, 12, (S, NV)).astype(np.int8)
+        sel_cls[: S // 10] = -1                                                    # empty scenes: all fill values
+        sel_ego = np.stack([rng.uniform(-30, 12, S), rng.uniform(-60, 30, S)], 1).astype(np.float32)
+        sel_light = (rng.random(S) < 0.3).astype(np.int64)
+        sel_virtual = rng.random(S) < 0.2
+        sel_out = []
+        for i in range(S):
+            env.ego_dynamics = dict(x=sel_ego[i, 0], y=sel_ego[i, 1])
+            env.v_light = int(sel_light[i])
+            env.virtual_red_light_vehicle = bool(sel_virtual[i])
+            env.all_vehicles = [dict(x=float(v[0]), y=float(v[1]), v=float(v[2]), phi=float(v[3]), l=4.8, w=2.0,
+                                     route=route[classes[c]] if c >= 0 else ('9o', '9i'))
+                                for v, c in zip(sel_veh[i], sel_cls[i])]
+            sel_out.append(env._construct_veh_vector_short())
+        out.update(sel_veh=sel_veh, sel_cls=sel_cls, sel_ego=sel_ego, sel_light=sel_light,
+                   sel_virtual=sel_virtual, sel_out=np.array(sel_out, np.float32))
         np.savez_compressed(os.path.join(HERE, 'env_%s.npz' % task), **out)
         print(task, 'done codes', np.bincount(out['done_code'], minlength=7))
 

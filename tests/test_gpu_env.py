@@ -159,3 +159,47 @@ def test_judge_done_against_reference_methods(e2e, task):
     got = np.where(g['v_light'] != 0, codes[1], codes[0])
     ok = margin > 1e-3
     assert ok.mean() > 0.95 and (got[ok] == g['done_code'][ok]).all()
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_vehicle_selection(e2e, task):
+    """k_select_vehicles against the goldens of the UNMODIFIED _construct_veh_vector_short
+    (bit-exact: the outputs are copies of inputs or fill constants) and, on 20000 random scenes,
+    against the oracle."""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, 'env_%s.npz' % task), allow_pickle=False))
+    env = e2e.CrossroadEnd2end(task, num_envs=len(g['sel_out']))
+    got = np.zeros_like(g['sel_out'])
+    for vl in (0, 1):                       # v_light is a scalar of the call: run both, pick per scene
+        env.v_light = vl
+        res = env.construct_veh_vectors(g['sel_veh'], g['sel_cls'], g['sel_ego'], g['sel_virtual']).numpy()
+        m = (g['sel_light'] != 0) == bool(vl)
+        got[m] = res[m]
+    assert np.array_equal(got.view(np.int32), g['sel_out'].view(np.int32))
+    # larger random batch against the oracle
+    rng = np.random.default_rng(8)
+    S, N = 20000, 24
+    veh = np.stack([np.round(rng.uniform(-45, 45, (S, N)) * 4) / 4, np.round(rng.uniform(-60, 50, (S, N)) * 4) / 4,
+                    rng.uniform(0, 8, (S, N)), rng.choice([0., 90., 180., -90.], (S, N))], 2).astype(np.float32)
+    cls = rng.integers(-1, 12, (S, N)).astype(np.int8)
+    ego = np.stack([rng.uniform(-30, 12, S), rng.uniform(-60, 30, S)], 1).astype(np.float32)
+    virt = rng.random(S) < 0.3
+    env.v_light = 0
+    res = env.construct_veh_vectors(veh, cls, ego, virt).numpy()
+    for i in rng.choice(S, 1500, replace=False):
+        want = orc.select_interested_vehicles(veh[i], cls[i], ego[i, 0], ego[i, 1], task, 0, bool(virt[i]))
+        assert np.array_equal(res[i].view(np.int32), want.view(np.int32)), i
+    # the single-env method with the reference's list-of-dicts format
+    one = e2e.CrossroadEnd2end(task)
+    one.reset()
+    names = {c: r for c, r in zip(e2e.ROUTE_CLASSES, [('1o', '4i'), ('1o', '3i'), ('1o', '2i'), ('2o', '1i'), ('2o', '4i'),
+                                                       ('2o', '3i'), ('3o', '2i'), ('3o', '1i'), ('3o', '4i'), ('4o', '3i'),
+                                                       ('4o', '2i'), ('4o', '1i')])}
+    assert [e2e.route_class(names[c]) for c in e2e.ROUTE_CLASSES] == list(range(12))
+    assert e2e.route_class(('2o', '1i'), 'R') == e2e.ROUTE_CLASSES.index('dl') and e2e.route_class(None) == -1
+    one.all_vehicles = [dict(x=float(v[0]), y=float(v[1]), v=float(v[2]), phi=float(v[3]), route=names[e2e.ROUTE_CLASSES[c]])
+                        for v, c in zip(veh[0], cls[0]) if c >= 0]
+    ex, ey = one.obs.numpy()[0, 3:5]
+    want = orc.select_interested_vehicles(veh[0][cls[0] >= 0], cls[0][cls[0] >= 0], ex, ey, task)
+    assert np.array_equal(one._construct_veh_vector_short().view(np.int32), want.view(np.int32))

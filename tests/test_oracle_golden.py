@@ -189,3 +189,17 @@ def test_gym_side_against_reference_methods(task):
     assert set(np.unique(code).tolist()) >= {0, 1, 2, 3, 4, 6}
     if task != 'right':
         assert (code == 5).any()
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_vehicle_selection_against_reference_method(task):
+    """select_interested_vehicles against the UNMODIFIED CrossroadEnd2end._construct_veh_vector_short
+    (E2E:340-464) on 300 random scenes per task (half-metre coordinates: many equal sort keys,
+    empty scenes, red-light virtual vehicles)."""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, 'env_%s.npz' % task), allow_pickle=False))
+    for i in range(len(g['sel_out'])):
+        got = orc.select_interested_vehicles(g['sel_veh'][i], g['sel_cls'][i], g['sel_ego'][i, 0], g['sel_ego'][i, 1],
+                                             task, int(g['sel_light'][i]), bool(g['sel_virtual'][i]))
+        _same(got, g['sel_out'][i], 'scene %d' % i)
