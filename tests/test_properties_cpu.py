@@ -1,0 +1,107 @@
+"""Property tests (hypothesis) of the oracle and the host-side helpers -- the invariants SURVEY.md
+section 4 lists: argmin tie rule, phi wrap, hinge continuity, zero penalty when far, action bounds,
+partition arithmetic.  CPU only."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from oracle import crossroad_oracle as orc
+from env_build_b200 import parallel as par
+from env_build_b200.endtoend import ROUTE_CLASSES, route_class
+
+f32 = np.float32
+finite = dict(allow_nan=False, allow_infinity=False, width=32)
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.floats(-539, 539, **finite), min_size=1, max_size=20))
+def test_phi_wrap_range_and_identity(xs):
+    x = np.array(xs, f32)
+    y = orc.deal_with_phi_diff(x)
+    assert ((y >= -180) & (y <= 180)).all()                       # one wrap each side covers |d| <= 540
+    inside = (x >= -180) & (x <= 180)
+    assert (y[inside] == x[inside]).all()
+    assert np.allclose(np.mod(y - x + 180, 360), 180, atol=1e-3)   # differs by a multiple of 360
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.tuples(st.floats(-3, 3, **finite), st.floats(-3, 3, **finite)), min_size=1, max_size=16))
+def test_action_scaling_bounds(acts):
+    s = orc.action_transformation(np.array(acts, f32))
+    assert (np.abs(s[:, 0]) <= f32(0.4) * f32(1.05)).all()
+    assert (s[:, 1] <= f32(2.25) * f32(1.05) - f32(0.75)).all() and (s[:, 1] >= f32(2.25) * f32(-1.05) - f32(0.75)).all()
+    inner = np.abs(np.array(acts, f32)).max(1) <= 1.05
+    assert np.array_equal(s[inner], np.stack([f32(0.4) * np.array(acts, f32)[inner, 0],
+                                              f32(2.25) * np.array(acts, f32)[inner, 1] - f32(0.75)], 1))
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.sampled_from(orc.TASKS), st.integers(0, 2), st.integers(2, 300))
+def test_argmin_first_minimum_on_ties(task, pi, k):
+    """A query exactly half-way between two consecutive every-10th waypoints of a straight piece is
+    equidistant in fp32: the LOWER index must win (tf.argmin / np.argmin rule, DM:712-714); nudging
+    it towards the upper waypoint flips the answer."""
+    paths = orc.construct_ref_paths(task)[0]
+    rp = orc.ReferencePath(task, pi, path_list=paths)
+    x, y = rp.path[0], rp.path[1]
+    k = min(k, len(x) // 10 - 2)
+    a, b = 10 * k, 10 * (k + 1)
+    if x[a] != x[b] and y[a] != y[b]:
+        return                                                    # not on an axis-parallel piece
+    qx, qy = (x[a] + x[b]) / f32(2), (y[a] + y[b]) / f32(2)
+    d = orc._sq(f32(qx) - x[[a, b]]) + orc._sq(f32(qy) - y[[a, b]])
+    idx, _ = rp.find_closest_point(np.array([qx], f32), np.array([qy], f32))
+    if d[0] == d[1]:
+        assert idx[0] == a
+    else:
+        assert idx[0] == (a if d[0] < d[1] else b)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.sampled_from(orc.TASKS), st.integers(0, 2 ** 31 - 1))
+def test_zero_collision_penalty_when_far_and_continuity(task, seed):
+    rng = np.random.default_rng(seed)
+    V, B = orc.VEH_NUM[task], 16
+    obs = np.zeros((B, 9 + 4 * V), f32)
+    obs[:, 3:5] = rng.uniform(-30, 30, (B, 2))
+    obs[:, 5] = rng.uniform(-180, 180, B)
+    ang = rng.uniform(0, 2 * np.pi, (B, V))
+    dist = rng.uniform(6.4, 60, (B, V))                           # centre distance > 3.5 + 2 * 1.4
+    veh = obs[:, 9:].reshape(B, V, 4)
+    veh[:, :, 0] = obs[:, 3:4] + dist * np.cos(ang)
+    veh[:, :, 1] = obs[:, 4:5] + dist * np.sin(ang)
+    veh[:, :, 3] = rng.uniform(-180, 180, (B, V))
+    r = orc.compute_rewards(obs, np.zeros((B, 2), f32), task)
+    assert (r[5]['veh2veh4training'] == 0).all() and (r[3] == 0).all()
+    # hinge continuity: pull one vehicle to just inside the 3.5 m gate of the front circles
+    o2 = obs.copy()
+    o2[:, 5] = 0.0                                                # ego heading +x: its rear circle is 2.8 m further
+    th = o2[:, 5] * np.pi / 180
+    fx, fy = o2[:, 3] + 1.4 * np.cos(th), o2[:, 4] + 1.4 * np.sin(th)
+    o2[:, 9], o2[:, 10], o2[:, 12] = fx + (3.5 - 1e-3) + 1.4, fy, 0.0      # vehicle rear circle 3.499 m from ego front
+    r2 = orc.compute_rewards(o2, np.zeros((B, 2), f32), task)
+    assert (r2[5]['veh2veh4training'] >= 0).all() and r2[5]['veh2veh4training'].max() < 1e-4
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.floats(0, 30, **finite), st.floats(-180, 180, **finite), st.floats(-3, 1.5, **finite))
+def test_f_xu_lateral_fixed_point(vx, phi, ax):
+    """v_y = r = steer = 0 stays a fixed point of the lateral states (DM:74-78)."""
+    nxt, _ = orc.f_xu(np.array([[vx, 0, 0, 1, 2, phi]], f32), np.array([[0, ax]], f32), 0.1)
+    assert nxt[0, 1] == 0 and nxt[0, 2] == 0 and abs(nxt[0, 5] - f32(phi)) <= 4e-5 * max(1.0, abs(phi))
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(0, 10 ** 7), st.integers(1, 16))
+def test_shard_bounds(B, W):
+    cuts = [par.shard_bounds(B, W, r) for r in range(W)]
+    assert cuts[0][0] == 0 and cuts[-1][1] == B and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+    sizes = [b - a for a, b in cuts]
+    assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+
+def test_route_class_mapping():
+    for ex, arms in (('D', '1234'), ('R', '2341'), ('U', '3412'), ('L', '4123')):
+        for ci, name in enumerate(ROUTE_CLASSES):
+            a, b = 'drul'.index(name[0]), 'drul'.index(name[1])
+            assert route_class((arms[a] + 'o', arms[b] + 'i'), ex) == ci
+    assert route_class(('1o', '1i')) == -1 and route_class(('1i', '2o')) == -1 and route_class(None) == -1
