@@ -326,6 +326,32 @@ def run_ours(args):
                 'note': 'vehicle sin/cos from the special-function unit (abs err 2^-21.4); within the 1e-5 '
                         'tolerance but not the default build; NOT the headline'}
         del rf
+    # ---- N > 1: the batch lives on rank 0; NCCL scatters the row blocks and gathers the returns
+    sharded = None
+    if world > 1:
+        from env_build_b200.parallel import ShardedRollout
+        Bg = world * B
+        sr = ShardedRollout(lambda b: RolloutGraph(model, b, V, H), Bg, D, H, dev)
+        if rank == 0:
+            _, g_obs, g_ref, g_tape = make_inputs(Bg, 4242)
+            full = [torch.from_numpy(g_obs).to(dev), torch.from_numpy(g_ref).to(dev), torch.from_numpy(g_tape).to(dev)]
+        else:
+            full = [None, None, None]
+        ret = {}
+
+        def sharded_step():
+            sr.scatter(*full)
+            sr.run()
+            ret['r'] = sr.gather_returns()
+
+        ks = max(3, min(K, 10))
+        ms_s = timed(sharded_step, 2, ks)
+        sharded = {'value': Bg * H * ks / (ms_s / 1e3), 'unit': 'env-steps/s', 'ms_per_step': ms_s / ks,
+                   'scatter_bytes_per_step': int(Bg * (D * 4 + 4 + H * 8)), 'gather_bytes_per_step': int(Bg * 20),
+                   'note': 'global batch of %d rows resident on rank 0: NCCL scatter of observations, path indexes '
+                           'and the action tape, %d-step rollout on every rank, NCCL gather of the per-row returns '
+                           '(sum over steps of the five outputs)' % (Bg, H)}
+        del sr, full
     t1 = time.perf_counter()
     clocks = sampler.stop(t0, t1) if sampler else None     # sampled over all GPU legs above
     cpu = None
@@ -356,7 +382,7 @@ def run_ours(args):
                              'bytes_per_launch': BYTES_PER_ENV_STEP * B,
                              'note': 'algorithmic bytes (8*D+32)*B per launch; at this batch the obs ping-pong '
                                      'fits L2, see large_batch for the HBM-bound rate'},
-                'large_batch': extra or None, 'fast_trig_option': fast,
+                'large_batch': extra or None, 'fast_trig_option': fast, 'sharded_from_rank0': sharded,
                 'cpu_baseline': cpu}
         emit(line)
     if world > 1:

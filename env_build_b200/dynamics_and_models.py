@@ -444,6 +444,25 @@ class EnvironmentModel(object):  # all tensors
         self.last_out5 = out5            # [5, B]: the five returned vectors as one tensor
         return (_wrap(nxt),) + tuple(_wrap(t) for t in out5.unbind(0))
 
+    def candidate_observations(self, obses):
+        """The multi-path evaluation pattern of the reference's online decision step
+        (hier_decision.py:112-119, multi_ego.py:98-114): every row is repeated once per reference
+        path with its tracking columns re-projected onto that path (what `env.set_traj(path);
+        env._get_obs()` yields, E2E:285-303).  Returns (obs [P*B, D] ordered path-major, ref_indexes
+        [P*B]); feed them to `reset(obs, ref_indexes)` with mode='training' to roll all candidates
+        out in one launch per step."""
+        obs = self._adopt(obses)
+        B, D = obs.shape
+        P = len(self.ref_path.path_list)
+        out = padded_rows(P * B, D, self._veh_off, obs.device)
+        ref = torch.arange(P, dtype=torch.int32, device=obs.device).repeat_interleave(B)
+        for p in range(P):
+            out[p * B:(p + 1) * B] = obs
+        trk = self.ref_path.tracking_error_vector(out[:, 3], out[:, 4], out[:, 5], out[:, 0], self.num_future_data,
+                                                  ref_indexes=ref)
+        out[:, 6:6 + trk.shape[1]] = _raw(trk)
+        return _wrap(out), _wrap(ref)
+
     def _action_transformation_for_end2end(self, actions):  # [-1, 1]
         act = _rows(to_device(actions), 'actions', 2).contiguous()
         out = torch.empty_like(act)

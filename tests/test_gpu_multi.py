@@ -1,0 +1,61 @@
+"""Row sharding over GPUs with NCCL (env_build_b200/parallel.py).  Needs >= 2 GPUs; skipped otherwise.
+Run on a multi-GPU box with:  python -m pytest tests/test_gpu_multi.py -m gpu"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, B, out_path):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        from env_build_b200 import synthetic as syn
+        from env_build_b200.dynamics_and_models import EnvironmentModel
+        from env_build_b200.parallel import ShardedRollout
+        from env_build_b200.rollout import RolloutGraph
+        task, V, H = 'straight', 9, 5
+        model = EnvironmentModel(task, mode='training')
+        sr = ShardedRollout(lambda b: RolloutGraph(model, b, V, H), B, 45, H, dev)
+        if rank == 0:
+            rng = np.random.default_rng(11)
+            ref = syn.make_ref_indexes(rng, B)
+            obs = syn.make_obs(rng, B, task, V, model.ref_path.path_list, ref)
+            tape = syn.make_actions(rng, H, B)
+            sr.scatter(torch.from_numpy(obs).to(dev), torch.from_numpy(ref).to(dev), torch.from_numpy(tape).to(dev))
+        else:
+            sr.scatter()
+        sr.run()
+        ret = sr.gather_returns()
+        if rank == 0:
+            # single-GPU result on the whole batch: shard invariance must be bit-exact
+            one = RolloutGraph(model, B, V, H)
+            one.load(obs, ref, tape)
+            one.run()
+            want = one.out5.sum(0).t().contiguous()
+            np.save(out_path, np.stack([ret.cpu().numpy(), want.cpu().numpy()]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('B', [4099])
+def test_sharded_rollout_nccl(tmp_path, B):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip('needs >= 2 GPUs')
+    world = 2
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / 'ret.npy')
+    mp.spawn(_worker, args=(world, port, B, out), nprocs=world, join=True)
+    got, want = np.load(out)
+    assert got.shape == (B, 5) and np.array_equal(got.view(np.int32), want.view(np.int32))

@@ -473,3 +473,36 @@ def test_fast_trig_option_within_tolerance(dm):
     close(fast[0][:, 9:], om.compute_next_obses(obs, sc)[:, 9:])
     bits_equal(fast[0][:, :9], exact[0][:, :9])                 # the ego path is untouched
     print('fast-trig max |dx| vs exact kernel: %.3g' % np.abs(fast[0] - exact[0]).max())
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_candidate_paths_shield_rollout(dm, task):
+    """The reference's decision pattern (hier_decision.py:89-119): one observation per candidate path,
+    then a 5-step shield rollout of every candidate -- here all 3B candidates in one batch."""
+    from env_build_b200 import synthetic as syn
+    rng = np.random.default_rng(21)
+    B, V = 500, orc.VEH_NUM[task]
+    model = dm.EnvironmentModel(task, mode='training')
+    paths = model.ref_path.path_list
+    obs = syn.make_obs(rng, B, task, V, paths, 0)
+    cand, ref = model.candidate_observations(obs)
+    assert cand.shape == (3 * B, obs.shape[1]) and ref.numpy().tolist() == [0] * B + [1] * B + [2] * B
+    c = cand.numpy()
+    for p in range(3):                                            # env.set_traj(path); env._get_obs()
+        rp = orc.ReferencePath(task, p, path_list=paths)
+        want = rp.tracking_error_vector(obs[:, 3], obs[:, 4], obs[:, 5], obs[:, 0], 0)
+        bits_equal(c[p * B:(p + 1) * B, 6:9], want)
+        bits_equal(c[p * B:(p + 1) * B, :6], obs[:, :6])
+        bits_equal(c[p * B:(p + 1) * B, 9:], obs[:, 9:])
+    model.reset(cand, ref)
+    prev = c
+    unsafe = torch.zeros(3 * B, device='cuda')
+    unsafe_o = np.zeros(3 * B, np.float32)
+    for t in range(5):                                            # is_safe (hier_decision.py:93-97)
+        a = syn.make_actions(rng, 1, 3 * B)[0]
+        res = model.rollout_out(a)
+        unsafe += res[4]
+        unsafe_o += orc.compute_rewards(prev, orc.action_transformation(a), task)[3]     # teacher forced
+        prev = res[0].numpy()
+    close(unsafe.cpu().numpy(), unsafe_o)
+    assert ((unsafe.cpu().numpy() > 0) == (unsafe_o > 0)).all()
