@@ -326,6 +326,17 @@ def run_ours(args):
                 'note': 'vehicle sin/cos from the special-function unit (abs err 2^-21.4); within the 1e-5 '
                         'tolerance but not the default build; NOT the headline'}
         del rf
+    # ---- open-loop horizon-fused mode (ce2e_rollout_horizon): a DIFFERENT mode, reported apart
+    fused = None
+    if world == 1:
+        rh = RolloutGraph(model, B, V, H, fused=True)
+        rh.load(obs, ref, tape)
+        ms_h = timed(rh.run, 3, K)
+        fused = {'value': B * H * K / (ms_h / 1e3), 'unit': 'env-steps/s', 'ms_per_rollout': ms_h / K,
+                 'note': 'one launch for all %d steps of an open-loop action tape, tile state resident on chip; '
+                         'per-step bytes are only actions + the five outputs, so the per-step HBM roofline does '
+                         'not apply; results bit-identical to the per-step launches; NOT the headline' % H}
+        del rh
     # ---- N > 1: the batch lives on rank 0; NCCL scatters the row blocks and gathers the returns
     sharded = None
     if world > 1:
@@ -382,7 +393,8 @@ def run_ours(args):
                              'bytes_per_launch': BYTES_PER_ENV_STEP * B,
                              'note': 'algorithmic bytes (8*D+32)*B per launch; at this batch the obs ping-pong '
                                      'fits L2, see large_batch for the HBM-bound rate'},
-                'large_batch': extra or None, 'fast_trig_option': fast, 'sharded_from_rank0': sharded,
+                'large_batch': extra or None, 'fast_trig_option': fast, 'horizon_fused_mode': fused,
+                'sharded_from_rank0': sharded,
                 'cpu_baseline': cpu}
         emit(line)
     if world > 1:

@@ -59,6 +59,8 @@ SIGNATURES = {
     'ce2e_rollout_step_backward': (_i, [_vp, _i, _vp, _vp, _i64, _vp, _i, _i, _vp, _i64, _vp, _vp, _i64, _vp, _i64,
                                         _vp]),
     'ce2e_select_vehicles': (_i, [_i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i64, _i64, _vp]),
+    'ce2e_rollout_horizon': (_i, [_vp, _i, _vp, _vp, _i64, _vp, _c.POINTER(TurnClasses), _i, _i, _i, _vp, _i64, _vp,
+                                  _i64, _vp]),
     'ce2e_ss': (_i, [_vp, _i64, _vp, _i64, _i, _i, _d, _vp, _i64, _vp]),
 }
 

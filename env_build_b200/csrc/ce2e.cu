@@ -179,6 +179,7 @@ struct StepParams {
     float *act_scaled_out;
     int64_t ld_in, ld_out, B;
     int task, path_index, V_in, V_out, n_future, flags;
+    int horizon;                 // FUSED kernels: steps per launch (act = tape [H,B,2], out5 = [H,5,B])
     ce2e_turn_classes turn;
 };
 
@@ -188,12 +189,16 @@ constexpr int RPW = 16;                  // rows per warp tile: two lanes per ro
 constexpr int VPL = 4;                   // vehicles per lane and staged chunk (16 B each)
 constexpr int QCAP = 24;                 // hinge queue entries per lane; flushed before it can overflow
 
-struct WarpScratch {
-    // double-buffered vehicle chunk: lane l owns floats [16 l, 16 l + 16); its vehicle e sits at
-    // float4 index e ^ ((l >> 1) & 3) (swizzle: lane-strided LDS.128 without bank conflicts)
-    float vbuf[2][32 * 4 * VPL];
+constexpr int FUSED_MAX_CHUNKS = 4;      // horizon-fused mode keeps all vehicle chunks resident: V <= 32
+template <int NBUF>
+struct WarpScratchT {
+    // vehicle chunk buffers (2: double buffering; FUSED_MAX_CHUNKS: the whole row, resident across steps):
+    // lane l owns floats [16 l, 16 l + 16); its vehicle e sits at float4 index e ^ ((l >> 1) & 3)
+    // (swizzle: lane-strided LDS.128 without bank conflicts)
+    float vbuf[NBUF][32 * 4 * VPL];
     float queue[QCAP * 32];              // [entry][lane]: squared distances inside the 3.5 m gate
 };
+typedef WarpScratchT<2> WarpScratch;
 
 __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
@@ -278,11 +283,17 @@ __device__ __forceinline__ void candidate_range(const GridView &gv, int p, int n
 //                  end of the tile, in the reference's order (vehicle, ego circle, vehicle circle).
 //                  veh2veh = (sum over the first half) + (sum over the second half): a fixed
 //                  order, independent of the batch size.
-template <bool REW, bool NEXT, bool FAST = false>
-__global__ void __launch_bounds__(STEP_THREADS, 2)
+// FUSED = true (ce2e_rollout_horizon): the warp keeps its tile's whole observation state on chip
+// (vehicles in FUSED_MAX_CHUNKS shared-memory chunk buffers, ego + tracking columns in registers)
+// and runs P.horizon steps of an open-loop action tape back to back; only the actions are read and
+// the five outputs written per step, the observations once at the start / end.  Same arithmetic
+// in the same order as `horizon` separate launches.
+template <bool REW, bool NEXT, bool FAST = false, bool FUSED = false>
+__global__ void __launch_bounds__(STEP_THREADS, FUSED ? 1 : 2)
 k_model_step(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // shared layout: WarpScratch[WARPS] | float2 xy[n_paths*stride] | float phi[n_paths*stride]
+    typedef WarpScratchT<FUSED ? FUSED_MAX_CHUNKS : 2> WarpScratch;
     WarpScratch *s_scr = reinterpret_cast<WarpScratch *>(smem_raw);
     float2 *s_xy = reinterpret_cast<float2 *>(s_scr + STEP_WARPS);
     float *s_phi = reinterpret_cast<float *>(s_xy + (size_t)P.pv.n_paths * P.pv.stride);
@@ -360,7 +371,11 @@ k_model_step(const __grid_constant__ StepParams P) {
             }
             cp_async_commit();
         };
-        if (n_chunks > 0) stage(0, 0);
+        if (FUSED) {
+            for (int ch = 0; ch < n_chunks; ++ch) stage(ch, ch);      // the whole row, once
+        } else if (n_chunks > 0) {
+            stage(0, 0);
+        }
         // ---------------- ego phase ----------------
         float e9[9];
         if (vec_in && veh_off == 9) {           // o[1] is 16 B aligned: 1 scalar + 2 vector loads
@@ -373,8 +388,12 @@ k_model_step(const __grid_constant__ StepParams P) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) e9[i] = o[i];
         }
+        const int n_steps = FUSED ? P.horizon : 1;
+        for (int step = 0; step < n_steps; ++step) {
+        const float *act_t = P.act + (FUSED ? (int64_t)step * 2 * P.B : 0);
+        const bool last_step = !FUSED || step == n_steps - 1;
         const float vx = e9[0], vy = e9[1], r = e9[2], x = e9[3], y = e9[4], phi_deg = e9[5];
-        float steer = P.act[2 * rr], a_x = P.act[2 * rr + 1];
+        float steer = act_t[2 * rr], a_x = act_t[2 * rr + 1];
         if (P.flags & F_ACT_NORM) action_transform(steer, a_x, steer, a_x);
         const float phi = deg2rad(phi_deg);
         float s, c;
@@ -407,6 +426,7 @@ k_model_step(const __grid_constant__ StepParams P) {
                 d[9 * B] = 0.05f * devi_v; d[10 * B] = 0.8f * devi_y; d[11 * B] = 30.0f * devi_phi;
             }
         }
+        float e9n[9];
         if (NEXT && (h == 1 || !REW)) {                                  // dynamics lane
             float nxt[6];
             f_xu_next(P.dyn, vx, vy, r, x, y, phi, s, c, steer, a_x, nxt);
@@ -425,7 +445,16 @@ k_model_step(const __grid_constant__ StepParams P) {
             float best;
             int bi;
             scan_min(t_xy, k0, k1, nxt[3], nxt[4], best, bi);
-            if (valid && h == 1) {
+            if (FUSED) {                                                  // state for the next step
+                float t9[3] = {0.0f, 0.0f, 0.0f};
+                if (p_ok)
+                    tracking_from_index(t_xy, s_phi + (size_t)p * P.pv.stride, P.pv.L[p], P.pv.tail[p],
+                                        P.task, bi, nxt[3], nxt[4], nxt[5], nxt[0], 0, t9);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) e9n[i] = nxt[i];
+                e9n[6] = t9[0]; e9n[7] = t9[1]; e9n[8] = t9[2];
+            }
+            if (valid && h == 1 && last_step) {
                 float *q = P.obs_out + row * P.ld_out;
                 float t9[3];
                 if (p_ok) {
@@ -469,13 +498,19 @@ k_model_step(const __grid_constant__ StepParams P) {
             }
             qa = q_lane;
         };
-        for (int ch = 0; ch < n_chunks; ++ch) {
-            const int b = ch & 1;
-            float *buf = scr.vbuf[b];
-            if (ch + 1 < n_chunks) stage(ch + 1, b ^ 1);
-            else cp_async_commit();
-            cp_async_wait<1>();
+        if (FUSED && step == 0) {
+            cp_async_wait<0>();
             __syncwarp();
+        }
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const int b = FUSED ? ch : (ch & 1);
+            float *buf = scr.vbuf[b];
+            if (!FUSED) {
+                if (ch + 1 < n_chunks) stage(ch + 1, b ^ 1);
+                else cp_async_commit();
+                cp_async_wait<1>();
+                __syncwarp();
+            }
             float4 *slot = reinterpret_cast<float4 *>(buf + lane * (4 * VPL));
             const int j0 = h * H + ch * VPL;                // this lane's first vehicle of the chunk
             const int j_end = h ? P.V_in : min(H, P.V_in);  // end of this lane's half
@@ -497,7 +532,7 @@ k_model_step(const __grid_constant__ StepParams P) {
             }
             if (REW && __any_sync(0xffffffffu, (int)(qa - q_lane) > (QCAP - 4 * VPL) * 128)) flush();
             __syncwarp();
-            if (NEXT) {
+            if (NEXT && last_step) {
                 float *dst = g_out + ch * (4 * VPL);
                 const float *src = buf + p_soff;
                 if (vec_out && rows_here == RPW && H + (ch + 1) * VPL <= P.V_out) {
@@ -531,7 +566,7 @@ k_model_step(const __grid_constant__ StepParams P) {
             const float re_o = __shfl_xor_sync(0xffffffffu, v2v_re, 1);
             if (valid && h == 0) {
                 const float tr = v2v_tr + tr_o, re = v2v_re + re_o;
-                float *o5 = P.out5;
+                float *o5 = P.out5 + (FUSED ? (int64_t)step * 5 * P.B : 0);
                 o5[row] = rewards;
                 o5[P.B + row] = tr + v2r_tr;                              // DM:299
                 o5[2 * P.B + row] = re + v2r_re;                          // DM:300
@@ -544,6 +579,11 @@ k_model_step(const __grid_constant__ StepParams P) {
                 }
             }
         }
+        if (FUSED) {                              // next step's ego + tracking columns: from the dynamics lane
+#pragma unroll
+            for (int i = 0; i < 9; ++i) e9[i] = __shfl_sync(0xffffffffu, e9n[i], lane | 1);
+        }
+        }                                         // step loop
     }
     if (tables_pending) {                     // a warp without tiles still owes the block its arrival
         cp_async_wait<0>();
@@ -572,25 +612,29 @@ int launch_model_step(StepParams &P, cudaStream_t st) {
     if (rc) return rc;
     if (P.ld_in > (1 << 24) || P.ld_out > (1 << 24)) return fail(CE2E_ERR_SHAPE, "row stride too large");
     const int64_t n_tiles = (P.B + RPW - 1) / RPW;
-    size_t smem = (size_t)P.pv.n_paths * P.pv.stride * 12 + STEP_WARPS * sizeof(WarpScratch);
+    const bool fused = P.horizon > 0;
+    size_t smem = (size_t)P.pv.n_paths * P.pv.stride * 12 +
+                  STEP_WARPS * (fused ? sizeof(WarpScratchT<FUSED_MAX_CHUNKS>) : sizeof(WarpScratch));
     if ((int)smem > di->max_smem_optin)
         return fail(CE2E_ERR_SHAPE, "path tables need %zu B of shared memory (max %d)", smem,
                     di->max_smem_optin);
     void (*kern)(const StepParams) = nullptr;
     const bool rew = P.flags & F_REWARD, next = P.flags & F_NEXT;
-    const bool fast = g_fast_trig && rew && next;
-    if (fast) kern = k_model_step<true, true, true>;
+    const bool fast = g_fast_trig && rew && next && !fused;
+    if (fused) kern = k_model_step<true, true, false, true>;
+    else if (fast) kern = k_model_step<true, true, true>;
     else if (rew && next) kern = k_model_step<true, true>;
     else if (rew) kern = k_model_step<true, false>;
     else kern = k_model_step<false, true>;
-    static thread_local size_t smem_set[4] = {0, 0, 0, 0};
-    size_t &set = smem_set[fast ? 3 : rew && next ? 0 : rew ? 1 : 2];
+    static thread_local size_t smem_set[5] = {0, 0, 0, 0, 0};
+    size_t &set = smem_set[fused ? 4 : fast ? 3 : rew && next ? 0 : rew ? 1 : 2];
     if (smem > set) {
         CE2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         set = smem;
     }
-    // two persistent blocks per SM; never more blocks than tiles
-    const int64_t blocks = n_tiles < 2 * di->sms ? n_tiles : 2 * di->sms;
+    // two persistent blocks per SM (one in the horizon-fused mode); never more blocks than tiles
+    const int64_t max_blocks = (fused ? 1 : 2) * (int64_t)di->sms;
+    const int64_t blocks = n_tiles < max_blocks ? n_tiles : max_blocks;
     // programmatic dependent launch: the next step's blocks may start (and stage their tables)
     // while this grid drains; they wait in griddepcontrol.wait before touching observations
     cudaLaunchConfig_t cfg;
@@ -1183,7 +1227,7 @@ int model_step_common(const ce2e_paths *paths, int task, int path_index, const i
                       const float *obs_in, int64_t ld_in, const float *act,
                       const ce2e_turn_classes *turn, int V_in, int V_out, int n_future,
                       float *obs_out, int64_t ld_out, float *out5, float *dict16,
-                      float *act_scaled_out, int64_t B, int flags, void *stream) {
+                      float *act_scaled_out, int64_t B, int flags, void *stream, int horizon = 0) {
     int rc;
     if ((rc = check_batch(B))) return rc;
     if ((rc = check_task(task))) return rc;
@@ -1220,6 +1264,7 @@ int model_step_common(const ce2e_paths *paths, int task, int path_index, const i
     P.dict16 = dict16; P.act_scaled_out = act_scaled_out;
     P.ld_in = ld_in; P.ld_out = ld_out; P.B = B;
     P.task = task; P.path_index = path_index; P.V_in = V_in; P.V_out = V_out; P.n_future = n_future;
+    P.horizon = horizon;
     const int veh_off = 6 + 3 * (n_future + 1);
     if (aligned16(obs_in + veh_off) && ld_in % 4 == 0) flags |= F_VEC_IN;
     if (obs_out && aligned16(obs_out + veh_off) && ld_out % 4 == 0) flags |= F_VEC_OUT;
@@ -1531,6 +1576,20 @@ int ce2e_select_vehicles(int task, const float *veh_all, const int8_t *route_cla
     k_select_vehicles<<<blocks_for(B * spec.n_modes, 128), 128, 0, (cudaStream_t)stream>>>(
         spec, task, veh_all, route_class, N, ego_xy, v_light, virtual_red, out, ld_out, B);
     return after_launch("k_select_vehicles");
+}
+
+int ce2e_rollout_horizon(const ce2e_paths *paths, int path_index, const int32_t *ref_idx,
+                         const float *obs_in, int64_t ld_in, const float *act_tape,
+                         const ce2e_turn_classes *turn, int V, int n_future, int H, float *obs_out,
+                         int64_t ld_out, float *out5, int64_t B, void *stream) {
+    if (!paths) return fail(CE2E_ERR_NULL, "paths handle is NULL");
+    if (H < 1 || H > (1 << 20)) return fail(CE2E_ERR_SHAPE, "bad horizon %d", H);
+    if (V > 4 * 2 * FUSED_MAX_CHUNKS)
+        return fail(CE2E_ERR_SHAPE, "the horizon-fused kernel keeps at most %d vehicles per row on chip",
+                    4 * 2 * FUSED_MAX_CHUNKS);
+    return model_step_common(paths, paths->task, path_index, ref_idx, obs_in, ld_in, act_tape, turn, V, V,
+                             n_future, obs_out, ld_out, out5, nullptr, nullptr, B,
+                             F_REWARD | F_NEXT | F_ACT_NORM, stream, H);
 }
 
 int ce2e_ss(const float *obs, int64_t ld, const float *next_obs, int64_t ld_next, int V,

@@ -23,7 +23,10 @@ class RolloutGraph(object):
                                      veh2veh4real, veh2road4real per step) and .final_obs [B,D]
     """
 
-    def __init__(self, model, B, V, H, use_graph=True):
+    def __init__(self, model, B, V, H, use_graph=True, fused=False):
+        """fused=True: ONE launch of the horizon-fused kernel (ce2e_rollout_horizon: the tile's state
+        stays on chip across the H steps) instead of H launches; same results, V <= 32."""
+        self.fused = bool(fused)
         self.model, self.B, self.V, self.H = model, int(B), int(V), int(H)
         if len(model.veh_mode_list) != V:
             raise ValueError('the model predicts %d vehicles, rows hold %d' % (len(model.veh_mode_list), V))
@@ -57,6 +60,12 @@ class RolloutGraph(object):
         handle = m.ref_path.handle
         src = self.obs0
         ld = self.obs0.stride(0)
+        if self.fused:
+            dst = self.buf[(self.H - 1) % 2]
+            _lib.check(lib.ce2e_rollout_horizon(handle, path_index, ref, _ptr(src), ld, _ptr(self.tape),
+                                                ctypes.byref(m._turn), self.V, self.n, self.H, _ptr(dst), ld,
+                                                _ptr(self.out5), self.B, stream))
+            return
         for t in range(self.H):
             dst = self.buf[t % 2]
             _lib.check(lib.ce2e_rollout_step(handle, path_index, ref, _ptr(src), ld, _ptr(self.tape[t]),
@@ -67,7 +76,7 @@ class RolloutGraph(object):
     def run(self):
         if not self.use_graph:
             self._enqueue()
-            self.launches_per_run = self.H
+            self.launches_per_run = 1 if self.fused else self.H
             return
         if self._graph is None:
             self.model.ref_path.handle            # create the device tables outside the capture
@@ -83,6 +92,6 @@ class RolloutGraph(object):
             with torch.cuda.graph(g):
                 self._enqueue()
             self.launches_per_run = _lib.launch_count() - n1
-            assert self.launches_per_run == n1 - n0 == self.H
+            assert self.launches_per_run == n1 - n0 == (1 if self.fused else self.H)
             self._graph = g
         self._graph.replay()

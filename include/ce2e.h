@@ -205,6 +205,16 @@ int ce2e_select_vehicles(int task, const float *veh_all, const int8_t *route_cla
                          const float *ego_xy, int v_light, const int8_t *virtual_red, float *out,
                          int64_t ld_out, int64_t B, void *stream);
 
+/* H consecutive EnvironmentModel.rollout_out steps (DM:118-126) of an OPEN-LOOP action tape in one
+ * launch (the shield / MPC rollouts of hier_decision.py:89-97, multi_ego.py:187-197 with the actions
+ * known in advance): act_tape [H,B,2] normalised actions, out5 [H,5,B] the five outputs of every
+ * step, obs_out [B,D] the observations after the last step.  The tile's state stays on chip between
+ * steps; results are bit-identical to H calls of ce2e_rollout_step.  V <= 32.                   */
+int ce2e_rollout_horizon(const ce2e_paths *paths, int path_index, const int32_t *ref_idx,
+                         const float *obs_in, int64_t ld_in, const float *act_tape,
+                         const ce2e_turn_classes *turn, int V, int n_future, int H, float *obs_out,
+                         int64_t ld_out, float *out5, int64_t B, void *stream);
+
 /* EnvironmentModel.ss(obses, actions, lam) (DM:134-184): discrete barrier penalty.
  * obs/next_obs [B,D] rows with V vehicles each (next_obs from ce2e_rollout_step or
  * compute_next_obses); out [B].                                                           */

@@ -506,3 +506,31 @@ def test_candidate_paths_shield_rollout(dm, task):
         prev = res[0].numpy()
     close(unsafe.cpu().numpy(), unsafe_o)
     assert ((unsafe.cpu().numpy() > 0) == (unsafe_o > 0)).all()
+
+
+@pytest.mark.parametrize('task,V,mode', [('left', 32, 'training'), ('straight', 9, 'selecting'), ('right', 5, 'training'),
+                                         ('left', 0, 'training')])
+def test_horizon_fused_equals_step_by_step(dm, task, V, mode):
+    """ce2e_rollout_horizon (state resident on chip across H steps) is bit-identical to H launches of
+    ce2e_rollout_step: every step's five outputs and the final observations."""
+    from env_build_b200 import synthetic as syn
+    from env_build_b200.rollout import RolloutGraph
+    rng = np.random.default_rng(33)
+    B, H = 5003, 7
+    model = dm.EnvironmentModel(task, mode=mode, veh_mode_list=tiled(task, V))
+    model.ref_path.set_path(1)
+    ref = syn.make_ref_indexes(rng, B, out_of_range_frac=0.02)
+    obs = syn.make_obs(rng, B, task, V, model.ref_path.path_list, ref if mode == 'training' else 1)
+    tape = syn.make_actions(rng, H, B)
+    outs = []
+    for fused in (False, True):
+        g = RolloutGraph(model, B, V, H, use_graph=False, fused=fused)
+        g.load(obs, ref, tape)
+        g.run()
+        torch.cuda.synchronize()
+        outs.append((g.out5.cpu().numpy().copy(), g.final_obs.numpy().copy()))
+    bits_equal(outs[1][0], outs[0][0])
+    bits_equal(outs[1][1], outs[0][1])
+    with pytest.raises(ValueError):
+        m40 = dm.EnvironmentModel(task, mode=mode, veh_mode_list=tiled(task, 40))
+        RolloutGraph(m40, 64, 40, 3, use_graph=False, fused=True).run()
