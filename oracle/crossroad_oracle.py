@@ -18,6 +18,7 @@ What it restates (all citations into /root/reference/):
   endtoend.py:132-283, 501-507    Gym step: action scaling, next ego state, ego dynamics (corner
                                   points, r_bound), done logic, reward (gym_* functions)
   traffic.py:263-295              two-circle collision check
+  endtoend.py:340-464             interested-vehicle selection (select_interested_vehicles)
 
 Numerics policy: tensors are fp32; + - * / sqrt are the
 IEEE fp32 ops NumPy performs (one rounding each, no FMA), in the association
@@ -31,11 +32,16 @@ Third-party arithmetic absent from /root/reference: the `bezier` PyPI package
 (un-pinned; no requirements file).  Its published cubic evaluation
 (`evaluate_multi_barycentric`, float64) is restated in `_bezier_cubic`.
 
+A float64 PyTorch restatement of rollout_out for GRADIENT checks lives in oracle/torch_model.py.
+
 PARITY PIN: the reference holds no golden vectors or numeric asserts for this
 path, and TensorFlow cannot be installed here.  The
 oracle is pinned instead against the UNMODIFIED reference source executed on
 a NumPy-backed TensorFlow stand-in (tests/golden/make_golden.py ->
-tests/golden/*.npz; tests/test_oracle_golden.py requires bit-equality).  With
+tests/golden/*.npz; tests/test_oracle_golden.py requires bit-equality); the Gym-side
+functions (next ego state, ego dynamics, done logic, reward, vehicle selection) are
+pinned against the unmodified CrossroadEnd2end / Traffic METHODS run on import-only
+stand-ins for gym / traci / sumolib (tests/golden/make_golden_env.py -> env_*.npz).  With
 respect to a real TF2 run the parity is therefore "unpinned" at the level of
 TF's transcendental kernels (<= ~1 ulp of fp32).
 """
