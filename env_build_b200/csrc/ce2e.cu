@@ -626,8 +626,11 @@ int launch_model_step(StepParams &P, cudaStream_t st) {
     else if (rew && next) kern = k_model_step<true, true>;
     else if (rew) kern = k_model_step<true, false>;
     else kern = k_model_step<false, true>;
-    static thread_local size_t smem_set[5] = {0, 0, 0, 0, 0};
-    size_t &set = smem_set[fused ? 4 : fast ? 3 : rew && next ? 0 : rew ? 1 : 2];
+    // the opt-in shared-memory size is a per-device attribute of each kernel instantiation
+    static thread_local size_t smem_set[64][5] = {};
+    int dev = 0;
+    CE2E_CUDA(cudaGetDevice(&dev));
+    size_t &set = smem_set[dev & 63][fused ? 4 : fast ? 3 : rew && next ? 0 : rew ? 1 : 2];
     if (smem > set) {
         CE2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         set = smem;
@@ -1252,6 +1255,10 @@ int model_step_common(const ce2e_paths *paths, int task, int path_index, const i
         if (!ref_idx && (path_index < 0 || path_index >= paths->n_paths))
             return fail(CE2E_ERR_PATH, "path_index %d outside [0, %d)", path_index, paths->n_paths);
         if (obs_out == obs_in) return fail(CE2E_ERR_SHAPE, "obs_out must not alias obs_in");
+        int cur_dev = -1;
+        CE2E_CUDA(cudaGetDevice(&cur_dev));
+        if (cur_dev != paths->device)
+            return fail(CE2E_ERR_PATH, "path tables live on device %d, current device is %d", paths->device, cur_dev);
         P.pv = make_view(paths);
         P.gv = make_grid_view(paths);
         if (turn) P.turn = *turn;
