@@ -534,3 +534,63 @@ def test_horizon_fused_equals_step_by_step(dm, task, V, mode):
     with pytest.raises(ValueError):
         m40 = dm.EnvironmentModel(task, mode=mode, veh_mode_list=tiled(task, 40))
         RolloutGraph(m40, 64, 40, 3, use_graph=False, fused=True).run()
+
+
+def test_free_running_drift_report(dm):
+    """free-running H=25 (state fed back on the device, no teacher forcing), B=4096, V=8:
+    report the drift against the fp32 oracle and the number of nearest-waypoint flips.  sin/cos
+    differ by <= 1.5 ulp per call, so trajectories separate by a few ulp per step; a flip moves the
+    reference point by 10 samples (0.33 m) and shows up as a jump in the tracking columns."""
+    from env_build_b200 import synthetic as syn
+    rng = np.random.default_rng(20210316)
+    task, B, V, H = 'left', 4096, 8, 25
+    model = dm.EnvironmentModel(task, mode='training')
+    paths = model.ref_path.path_list
+    ref = syn.make_ref_indexes(rng, B)
+    obs = syn.make_obs(rng, B, task, V, paths, ref)
+    tape = syn.make_actions(rng, H, B)
+    om = orc.EnvironmentModel(task, mode='training', path_list=paths)
+    model.reset(obs, ref)
+    om.reset(obs, ref)
+    worst_ego, worst_veh, flips = 0.0, 0.0, np.zeros(B, bool)
+    for t in range(H):
+        g = model.rollout_out(tape[t])[0].numpy()
+        w = om.rollout_out(tape[t])[0]
+        flips |= np.abs(g[:, 6] - w[:, 6]) > 0.05
+        keep = ~flips
+        worst_ego = max(worst_ego, float(np.abs(g[keep, :6] - w[keep, :6]).max()))
+        worst_veh = max(worst_veh, float(np.abs(g[:, 9:] - w[:, 9:]).max()))
+    print('free-running H=25, B=%d: max |ego drift| %.3g, max |vehicle drift| %.3g, waypoint flips %d rows (%.3f %%)'
+          % (B, worst_ego, worst_veh, int(flips.sum()), 100.0 * flips.mean()))
+    assert worst_ego < 2e-4 and worst_veh < 2e-4 and flips.mean() < 0.01
+
+
+def test_fp64_shadow_accuracy(dm):
+    """How far do the fp32 kernel and the fp32 oracle each sit from a float64 evaluation of the same
+    op graph (oracle/torch_model.py)?  The kernel must not be further from the exact value than a few
+    times the oracle's own rounding error."""
+    from env_build_b200 import synthetic as syn
+    from oracle import torch_model as tm
+    rng = np.random.default_rng(20210317)
+    task, B, V = 'left', 3000, 8
+    model = dm.EnvironmentModel(task, mode='training')
+    paths = model.ref_path.path_list
+    ref = syn.make_ref_indexes(rng, B)
+    obs = syn.make_obs(rng, B, task, V, paths, ref)
+    act = syn.make_actions(rng, 1, B)[0]
+    model.reset(obs, ref)
+    got = [r.numpy() for r in model.rollout_out(act)]
+    om = orc.EnvironmentModel(task, mode='training', path_list=paths)
+    om.reset(obs, ref)
+    _, margin = om.compute_next_obses(obs, orc.action_transformation(act), return_margin=True)
+    want = om.rollout_out(act)
+    shadow = tm.rollout_out(torch.tensor(obs, dtype=torch.float64), torch.tensor(act, dtype=torch.float64), task, ref,
+                            paths, orc.VEHICLE_MODE_LIST[task])
+    ok = margin > 1e-3
+    names = ['next_obs', 'rewards', 'punish_train', 'punish_real', 'veh2veh4real', 'veh2road4real']
+    for name, g, w, s in zip(names, got, want, shadow):
+        s = s.numpy()
+        eg = np.abs(g[ok] - s[ok]) / (1.0 + np.abs(s[ok]))
+        ew = np.abs(w[ok] - s[ok]) / (1.0 + np.abs(s[ok]))
+        print('%-14s max scaled error vs float64: kernel %.3g   oracle %.3g' % (name, eg.max(), ew.max()))
+        assert eg.max() <= 4 * ew.max() + 2e-6
