@@ -98,6 +98,12 @@ class CpuArm(object):
         self.pool.map(_cpu_worker, self.jobs)
         return time.perf_counter() - t0
 
+    def one_thread_rate(self):
+        """env-steps/s of ONE process on its share (the reference pins TF to one thread)."""
+        t0 = time.perf_counter()
+        _cpu_worker(self.jobs[0])
+        return self.jobs[0][0].shape[0] * H / (time.perf_counter() - t0)
+
     def close(self):
         self.pool.close()
         self.pool.join()
@@ -391,8 +397,10 @@ def run_ours(args):
         while tot < 10.0 and n < 20:
             tot += arm.step()
             n += 1
+        one = arm.one_thread_rate()
         arm.close()
         cpu = {'value': arm.rows * H * n / tot, 'unit': 'env-steps/s', 'cores': arm.cores, 'kind': 'port',
+               'value_1_thread': one,
                'sample': '%d steps of %s' % (n, arm.describe()),
                'note': 'NumPy fp32 restatement of the reference algorithm (oracle/), one process per core'}
 
