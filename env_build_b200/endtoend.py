@@ -215,8 +215,13 @@ class CrossroadEnd2end(object):
         """E2E:200-256 on the current (or given) post-step observations -> (done_type, done) for one
         environment, (codes, done) tensors for a batch."""
         obs = self.obs if obs is None else self.env_model._adopt(np.atleast_2d(np.asarray(obs, np.float32)))
-        act = self.action if scaled_action is None else to_device(np.atleast_2d(np.asarray(scaled_action, np.float32)))
         B = obs.shape[0]
+        if scaled_action is not None:
+            act = to_device(np.atleast_2d(np.asarray(scaled_action, np.float32)))
+        elif self.action is not None:
+            act = self.action
+        else:                                   # right after reset(): miu_r = miu like E2E:111-113 (a_x = 0)
+            act = torch.zeros((B, 2), dtype=torch.float32, device=obs.device)
         done = torch.empty((B,), dtype=torch.int8, device=obs.device)
         _lib.check(_lib.load().ce2e_judge_done(_lib.TASK_ID[self.training_task], _ptr(obs), obs.stride(0) if B > 1 else
                                                max(obs.stride(0), obs.shape[1]), _ptr(act.contiguous()), self.veh_num,
