@@ -406,6 +406,37 @@ def test_full_size_properties(dm):
         close(a[sel], b)
 
 
+def test_offsets_beyond_4GiB(dm):
+    """Maximum sizes: 8 Mi rows x 144 floats = 4.8 GB per buffer, so byte offsets pass 2^31 and 2^32.
+    The big batch is a small one tiled on the device; every tile must reproduce the small batch's
+    results bit for bit (rows are independent, the kernel's summation order is fixed)."""
+    from env_build_b200 import synthetic as syn
+    from env_build_b200.dynamics_and_models import padded_rows
+    rng = np.random.default_rng(77)
+    task, V, Bs, reps = 'left', 32, 8192, 1024
+    model = dm.EnvironmentModel(task, mode='training', veh_mode_list=tiled(task, V))
+    ref = syn.make_ref_indexes(rng, Bs, out_of_range_frac=0.01)
+    obs = syn.make_obs(rng, Bs, task, V, model.ref_path.path_list, ref)
+    act = syn.make_actions(rng, 1, Bs)[0]
+    model.reset(obs, ref)
+    small = [r.clone() for r in model.rollout_out(act)]
+    B = Bs * reps
+    big = padded_rows(B, 137, 9, torch.device('cuda'))
+    assert big.stride(0) * 4 * B > (1 << 32)
+    big.unflatten(0, (reps, Bs)).copy_(torch.as_tensor(obs, device='cuda').unsqueeze(0).expand(reps, Bs, 137))
+    model.reset(big, torch.as_tensor(ref, device='cuda').repeat(reps))
+    del big
+    res = model.rollout_out(torch.as_tensor(act, device='cuda').repeat(reps, 1))
+    torch.cuda.synchronize()
+    assert res[0].shape == (B, 137)
+    for k in (0, 1, reps // 2 - 1, reps // 2, reps - 2, reps - 1):      # tiles on both sides of 2^31 and 2^32 B
+        assert torch.equal(res[0][k * Bs:(k + 1) * Bs], small[0]), k
+    for i in range(1, 6):
+        assert torch.equal(res[i].view(reps, Bs), small[i].unsqueeze(0).expand(reps, Bs)), i
+    del res
+    torch.cuda.empty_cache()
+
+
 def test_edge_cases_and_errors(dm):
     m = dm.EnvironmentModel('straight', mode='selecting')
     m.ref_path.set_path(0)
