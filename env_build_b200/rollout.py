@@ -21,12 +21,21 @@ class RolloutGraph(object):
     run()                            replay the graph (H launches); results in
                                      .out5 [H,5,B] (rewards, punish_train, punish_real,
                                      veh2veh4real, veh2road4real per step) and .final_obs [B,D]
+
+    Closed loop (the reference's shield pattern `actions = policy(obses); model.rollout_out(actions)`,
+    hier_decision.py:93-96): pass `policy`, a callable mapping the current observations (a [B,D]
+    CUDA tensor view, rows padded) to normalised actions [B,2] with capture-safe torch ops; it is
+    captured into the same graph between the step launches and the actions it chose are left in
+    .tape [H,B,2].
     """
 
-    def __init__(self, model, B, V, H, use_graph=True, fused=False):
+    def __init__(self, model, B, V, H, use_graph=True, fused=False, policy=None):
         """fused=True: ONE launch of the horizon-fused kernel (ce2e_rollout_horizon: the tile's state
-        stays on chip across the H steps) instead of H launches; same results, V <= 32."""
+        stays on chip across the H steps) instead of H launches; same results, V <= 32, open loop only."""
         self.fused = bool(fused)
+        self.policy = policy
+        if policy is not None and self.fused:
+            raise ValueError('the horizon-fused kernel needs the whole action tape in advance (no policy)')
         self.model, self.B, self.V, self.H = model, int(B), int(V), int(H)
         if len(model.veh_mode_list) != V:
             raise ValueError('the model predicts %d vehicles, rows hold %d' % (len(model.veh_mode_list), V))
@@ -68,6 +77,9 @@ class RolloutGraph(object):
             return
         for t in range(self.H):
             dst = self.buf[t % 2]
+            if self.policy is not None:
+                with torch.no_grad():
+                    self.tape[t].copy_(self.policy(src))
             _lib.check(lib.ce2e_rollout_step(handle, path_index, ref, _ptr(src), ld, _ptr(self.tape[t]),
                                              ctypes.byref(m._turn), self.V, self.V, self.n, _ptr(dst), ld,
                                              _ptr(self.out5[t]), None, self.B, stream))

@@ -625,3 +625,53 @@ def test_fp64_shadow_accuracy(dm):
         ew = np.abs(w[ok] - s[ok]) / (1.0 + np.abs(s[ok]))
         print('%-14s max scaled error vs float64: kernel %.3g   oracle %.3g' % (name, eg.max(), ew.max()))
         assert eg.max() <= 4 * ew.max() + 2e-6
+
+
+def test_closed_loop_policy_in_graph(dm):
+    """hier_decision.py:93-96 pattern `actions = policy(obses); model.rollout_out(actions)` captured as one
+    CUDA graph: bit-identical to stepping the public API by hand, and within tolerance of the oracle
+    driven by the recorded actions."""
+    from env_build_b200 import synthetic as syn
+    from env_build_b200.rollout import RolloutGraph
+    rng = np.random.default_rng(5)
+    task, B, V, H = 'left', 1500, 8, 5
+    model = dm.EnvironmentModel(task, mode='selecting')
+    obs = syn.make_obs(rng, B, task, V, model.ref_path.path_list, 1)
+    gen = torch.Generator(device='cuda').manual_seed(3)
+    w1 = torch.randn((41, 32), device='cuda', generator=gen) * 0.05
+    w2 = torch.randn((32, 2), device='cuda', generator=gen) * 0.3
+
+    def policy(o):
+        return torch.tanh(torch.tanh(o @ w1) @ w2)
+
+    model.ref_path.set_path(1)
+    g = RolloutGraph(model, B, V, H, policy=policy)
+    g.load(obs)
+    g.run()
+    g.load(obs)
+    g.run()                                            # a replay, not the capture pass
+    torch.cuda.synchronize()
+    tape, out5, final = g.tape.cpu().numpy(), g.out5.cpu().numpy(), g.final_obs.numpy()
+    assert np.abs(tape).max() <= 1.0 and np.abs(tape).std() > 0.05
+    # by hand through the public API
+    model.add_traj(obs, 1)
+    for t in range(H):
+        a = policy(torch.as_tensor(model.obses))
+        bits_equal(a.cpu().numpy(), tape[t])
+        res = model.rollout_out(a)
+        bits_equal(np.stack([r.numpy() for r in res[1:]]), out5[t])
+    bits_equal(res[0].numpy(), final)
+    # oracle driven by the recorded actions, re-seeded from the device observations every step
+    om = orc.EnvironmentModel(task, mode='selecting', path_list=model.ref_path.path_list)
+    model.add_traj(obs, 1)
+    cur = obs
+    for t in range(H):
+        om.add_traj(cur, 1)
+        want = om.rollout_out(tape[t])
+        res = model.rollout_out(tape[t])
+        for a, b in zip(res[1:], want[1:]):
+            close(a.numpy(), b)
+        close(res[0].numpy()[:, :6], want[0][:, :6])
+        cur = res[0].numpy()
+    with pytest.raises(ValueError):
+        RolloutGraph(model, B, V, H, fused=True, policy=policy)
