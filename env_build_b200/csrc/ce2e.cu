@@ -961,30 +961,72 @@ __device__ __forceinline__ void road_terms_grad(int task, float px, float py, fl
 
 __device__ __forceinline__ void pair_grad(float ex, float ey, float px, float py, float w_tr, float w_re,
                                           float &gx, float &gy) {
+    // d/dE of hinge^2: 2 (d - thr) (E - P) / d inside the threshold, else 0.  Branch free (few lanes
+    // of a warp are ever inside the gate); 1/d from the special-function unit -- gradients are checked
+    // against float64 autograd at 2e-3, not bit for bit.
     const float dx = ex - px, dy = ey - py;
     const float dd = dx * dx + dy * dy;
-    if (dd < 12.25f && dd > 0.0f) {
-        const float d = __fsqrt_rn(dd);
-        float k = 0.0f;
-        if (d - 3.5f < 0.0f) k += w_tr * 2.0f * (d - 3.5f);
-        if (d - 2.5f < 0.0f) k += w_re * 2.0f * (d - 2.5f);
-        k = k / d;
-        gx += k * dx;
-        gy += k * dy;
-    }
+    const float inv_d = rsqrtf(dd);
+    const float d = dd * inv_d;
+    const float k = (w_tr * fminf(d - 3.5f, 0.0f) + w_re * fminf(d - 2.5f, 0.0f)) * (2.0f * inv_d);
+    const bool in = dd < 12.25f && dd > 0.0f;
+    gx += in ? k * dx : 0.0f;
+    gy += in ? k * dy : 0.0f;
 }
 
-__global__ void k_model_step_bwd(const __grid_constant__ PathView pv, const __grid_constant__ GridView gv,
-                                 const __grid_constant__ DynConsts K, int task, int path_index,
-                                 const int32_t *__restrict__ ref_idx, const float *__restrict__ obs,
-                                 int64_t ld, const float *__restrict__ act_norm, int V, int n_future,
-                                 const float *__restrict__ g_next, int64_t ld_gn,
-                                 const float *__restrict__ g_out5, float *__restrict__ g_obs, int64_t ld_go,
-                                 float *__restrict__ g_act, int64_t B) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B) return;
+// TILED = false: one thread per row, scalar loads (any alignment).
+// TILED = true : the forward's decomposition -- a warp owns 16 rows, two lanes per row; lane h sums
+//                the collision gradient over vehicle half h, the halves' 16 B vehicle records
+//                streamed through shared memory with coalesced cp.async copies (double buffered);
+//                then lane 0 takes the reward / road terms and lane 1 the next-observation terms.
+//                Needs a 16 B aligned vehicle block, ld % 4 == 0.
+constexpr int BWD_WARPS = 8;
+template <bool TILED>
+__global__ void __launch_bounds__(TILED ? BWD_WARPS * 32 : 128, TILED ? 4 : 1)
+k_model_step_bwd(const __grid_constant__ PathView pv, const __grid_constant__ GridView gv,
+                 const __grid_constant__ DynConsts K, int task, int path_index,
+                 const int32_t *__restrict__ ref_idx, const float *__restrict__ obs,
+                 int64_t ld, const float *__restrict__ act_norm, int V, int n_future,
+                 const float *__restrict__ g_next, int64_t ld_gn,
+                 const float *__restrict__ g_out5, float *__restrict__ g_obs, int64_t ld_go,
+                 float *__restrict__ g_act, int64_t B) {
+    __shared__ __align__(16) float s_veh[TILED ? BWD_WARPS : 1][2][TILED ? 32 * 4 * VPL : 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = (int64_t)blockIdx.x * BWD_WARPS + warp;
+    int64_t i;
+    bool owner = true;                       // this thread writes the row's outputs
+    if (TILED) {
+        if (tile * RPW >= B) return;         // whole warp
+        const int64_t row = tile * RPW + (lane >> 1);
+        owner = row < B && (lane & 1) == 0;
+        i = row < B ? row : B - 1;
+    } else {
+        i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= B) return;
+    }
     const float *o = obs + i * ld;
     const int n_trk = 3 * (n_future + 1);
+    // TILED staging geometry (that of k_model_step): piece k of a lane = row (lane / 8) + 4 k of the
+    // tile, vehicle (lane % 4) of half (lane / 4) % 2 of the chunk; it lands in the slot of lane
+    // 2 * row + half at float4 index vehicle ^ (row % 4)
+    const int H = (V + 1) >> 1, n_chunks = (H + VPL - 1) / VPL;
+    const int rows_here = TILED ? (int)min((int64_t)RPW, B - tile * RPW) : 0;
+    const int p_row = lane >> 3, p_half = (lane >> 2) & 1, p_e = lane & 3;
+    const int p_veh = p_half * H + p_e;
+    const int p_soff = (2 * p_row + p_half) * (4 * VPL) + ((p_e ^ (p_row & 3)) << 2);
+    constexpr int PIECE_STRIDE = 8 * 4 * VPL;
+    const float *g_in = obs + (TILED ? tile * RPW : 0) * ld + (p_row * ld + 6 + n_trk + 4 * p_veh);
+    auto stage = [&](int ch, int b) {
+        if (p_veh + ch * VPL < (p_half ? V : min(H, V))) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (p_row + 4 * k < rows_here)
+                    cp_async16((unsigned)__cvta_generic_to_shared(&s_veh[TILED ? warp : 0][b][TILED ? p_soff + k * PIECE_STRIDE : 0]),
+                               g_in + ch * (4 * VPL) + 4 * k * ld);
+        }
+        cp_async_commit();
+    };
+    if (TILED && n_chunks > 0) stage(0, 0);          // in flight while the ego columns arrive
     const float vx = o[0], vy = o[1], r = o[2], x = o[3], y = o[4], phi_deg = o[5];
     const float a0 = act_norm[2 * i], a1 = act_norm[2 * i + 1];
     float steer, a_x;
@@ -1004,103 +1046,145 @@ __global__ void k_model_step_bwd(const __grid_constant__ PathView pv, const __gr
     const float g_dy = gR * (-1.6f * o[6]);
     const float g_dphi = gR * (-60.0f * D2R * D2R * o[7]);
     const float g_dv = gR * (-0.1f * o[8]);
-    gr += gR * (-0.04f * r);
-    gsteer += gR * (-10.0f * steer);
-    gax += gR * (-0.1f * a_x);
+    // TILED: lane h = 0 takes the reward + penalty terms, lane h = 1 the next-observation terms; the
+    // partial gradients are added at the end
+    const bool do_rew = !TILED || (lane & 1) == 0, do_next = !TILED || (lane & 1) == 1;
+    if (do_rew) {
+        gr += gR * (-0.04f * r);
+        gsteer += gR * (-10.0f * steer);
+        gax += gR * (-0.1f * a_x);
+    }
     // ---- collision and road penalties through the ego circle centres (DM:210-295)
     {
         const Circles ec = circle_centres(x, y, s, c);
         const float w_tr = gPtr, w_re_v = gPre + gV2V, w_re_r = gPre + gV2R;
         float gfx = 0.f, gfy = 0.f, grx = 0.f, gry = 0.f;
         const float *veh = o + 6 + n_trk;
-        for (int j = 0; j < V; ++j) {
-            const float *v = veh + 4 * j;
+        auto one_vehicle = [&](float vx_, float vy_, float vphi) {
             float vs, vc;
-            sincos_cw(deg2rad(v[3]), vs, vc);
-            const Circles w = circle_centres(v[0], v[1], vs, vc);
+            sincos_cw(deg2rad(vphi), vs, vc);
+            const Circles w = circle_centres(vx_, vy_, vs, vc);
             pair_grad(ec.fx, ec.fy, w.fx, w.fy, w_tr, w_re_v, gfx, gfy);
             pair_grad(ec.fx, ec.fy, w.rx, w.ry, w_tr, w_re_v, gfx, gfy);
             pair_grad(ec.rx, ec.ry, w.fx, w.fy, w_tr, w_re_v, grx, gry);
             pair_grad(ec.rx, ec.ry, w.rx, w.ry, w_tr, w_re_v, grx, gry);
-        }
-        road_terms_grad(task, ec.fx, ec.fy, w_tr, w_re_r, gfx, gfy);
-        road_terms_grad(task, ec.rx, ec.ry, w_tr, w_re_r, grx, gry);
-        gx += gfx + grx;
-        gy += gfy + gry;
-        // F = (x + l c, y + l s), R = (x - l c, y - l s);  d/dphi_deg = D2R * d/dtheta
-        gphi += D2R * CE2E_LWS * ((-s) * gfx + c * gfy + s * grx - c * gry);
-    }
-    // ---- next observation (DM:322-353)
-    const float *gn = g_next + i * ld_gn;
-    float nxt[6];
-    f_xu_next(K, vx, vy, r, x, y, phi, s, c, steer, a_x, nxt);
-    const float vx_raw = nxt[0];
-    nxt[0] = fminf(fmaxf(vx_raw, 0.0f), 35.0f);
-    float g_n[6];
+        };
+        if (TILED) {
+            const int h = lane & 1, swz = (lane >> 1) & 3;
+            const int j_end = h ? V : min(H, V);
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                if (ch + 1 < n_chunks) stage(ch + 1, (ch + 1) & 1);
+                else cp_async_commit();
+                cp_async_wait<1>();
+                __syncwarp();
+                const float4 *slot = reinterpret_cast<const float4 *>(&s_veh[warp][ch & 1][lane * (4 * VPL)]);
+                const int j0 = h * H + ch * VPL;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) g_n[k] = gn[k];
-    int p = ref_idx ? ref_idx[i] : path_index;
-    if (p >= 0 && p < pv.n_paths) {                                     // tracking' = T(x', y', phi', vx')
-        const float2 *t_xy = pv.xy + (size_t)p * pv.stride;
-        int k0, k1, bi;
-        float best;
-        candidate_range(gv, p, (pv.N[p] + 1) & ~1, nxt[3], nxt[4], k0, k1);
-        scan_min(t_xy, k0, k1, nxt[3], nxt[4], best, bi);
-        const float2 w = t_xy[bi];
-        const float ex = nxt[3], ey = nxt[4];
-        float ddx = 0.f, ddy = 0.f;                                     // d(two2one)/d(ex, ey) = -d(delta)
-        if (task == 0) {
-            const float rho = __fsqrt_rn(sq(ex + CE2E_HALF) + sq(ey + CE2E_HALF));
-            ddx = -(ex + CE2E_HALF) / rho; ddy = -(ey + CE2E_HALF) / rho;
-            if (ey < -CE2E_HALF) { ddx = -1.0f; ddy = 0.0f; }
-            if (ex < -CE2E_HALF) { ddx = 0.0f; ddy = -1.0f; }
-        } else if (task == 1) {
-            ddx = -1.0f;
+                for (int e = 0; e < VPL; ++e) {
+                    if (j0 + e < j_end) {
+                        const float4 v = slot[e ^ swz];
+                        one_vehicle(v.x, v.y, v.w);
+                    }
+                }
+                __syncwarp();
+            }
+            cp_async_wait<0>();
+            // the two halves of the row
+            gfx += __shfl_xor_sync(0xffffffffu, gfx, 1);
+            gfy += __shfl_xor_sync(0xffffffffu, gfy, 1);
+            grx += __shfl_xor_sync(0xffffffffu, grx, 1);
+            gry += __shfl_xor_sync(0xffffffffu, gry, 1);
         } else {
-            const float rho = __fsqrt_rn(sq(ex - CE2E_HALF) + sq(ey + CE2E_HALF));
-            ddx = (ex - CE2E_HALF) / rho; ddy = (ey + CE2E_HALF) / rho;
-            if (ey < -CE2E_HALF) { ddx = -1.0f; ddy = 0.0f; }
-            if (ex > CE2E_HALF) { ddx = 0.0f; ddy = 1.0f; }
+            for (int j = 0; j < V; ++j) one_vehicle(veh[4 * j], veh[4 * j + 1], veh[4 * j + 3]);
         }
-        (void)w;
-        g_n[3] += gn[6] * ddx;
-        g_n[4] += gn[6] * ddy;
-        g_n[5] += gn[7];
-        g_n[0] += gn[8];
-        for (int k = 0; k < n_future; ++k) {                             // (fx - x', fy - y', wrap(phi' - fphi))
-            g_n[3] -= gn[9 + 3 * k];
-            g_n[4] -= gn[10 + 3 * k];
-            g_n[5] += gn[11 + 3 * k];
+        if (do_rew) {
+            road_terms_grad(task, ec.fx, ec.fy, w_tr, w_re_r, gfx, gfy);
+            road_terms_grad(task, ec.rx, ec.ry, w_tr, w_re_r, grx, gry);
+            gx += gfx + grx;
+            gy += gfy + gry;
+            // F = (x + l c, y + l s), R = (x - l c, y - l s);  d/dphi_deg = D2R * d/dtheta
+            gphi += D2R * CE2E_LWS * ((-s) * gfx + c * gfy + s * grx - c * gry);
         }
     }
-    if (!(vx_raw >= 0.0f && vx_raw <= 35.0f)) g_n[0] = 0.0f;            // clip_by_value (DM:390)
-    // ---- back through f_xu (DM:73-81)
-    {
-        const float tau = K.tau;
-        // vx' = vx + tau (a_x + vy r)
-        gvx += g_n[0]; gvy += g_n[0] * tau * r; gr += g_n[0] * tau * vy; gax += g_n[0] * tau;
-        // vy' = N1 / D1
-        const float D1 = K.m * vx - K.Dv, vy1 = nxt[1];
-        const float k1 = g_n[1] / D1;
-        gvx += k1 * ((K.m * vy - K.tauCf * steer - 2.0f * K.taum * vx * r) - vy1 * K.m);
-        gvy += k1 * (K.m * vx);
-        gr += k1 * (K.tauK1 - K.taum * vx * vx);
-        gsteer += k1 * (-K.tauCf * vx);
-        // r' = N2 / D2
-        const float D2 = K.Dr - K.Iz * vx, r1 = nxt[2];
-        const float k2 = g_n[2] / D2;
-        gvx += k2 * ((-K.Iz * r + K.tauaCf * steer) + r1 * K.Iz);
-        gvy += k2 * (-K.tauK1);
-        gr += k2 * (-K.Iz * vx);
-        gsteer += k2 * (K.tauaCf * vx);
-        // x' = x + tau (vx c - vy s), y' = y + tau (vx s + vy c)
-        gx += g_n[3]; gy += g_n[4];
-        gvx += tau * (g_n[3] * c + g_n[4] * s);
-        gvy += tau * (-g_n[3] * s + g_n[4] * c);
-        gphi += D2R * tau * (g_n[3] * (-vx * s - vy * c) + g_n[4] * (vx * c - vy * s));
-        // phi' = phi + tau r 180/pi
-        gphi += g_n[5];
-        gr += g_n[5] * tau * (180.0f / CE2E_PI32);
+    if (do_next) {
+        // ---- next observation (DM:322-353)
+        const float *gn = g_next + i * ld_gn;
+        float nxt[6];
+        f_xu_next(K, vx, vy, r, x, y, phi, s, c, steer, a_x, nxt);
+        const float vx_raw = nxt[0];
+        nxt[0] = fminf(fmaxf(vx_raw, 0.0f), 35.0f);
+        float g_n[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g_n[k] = gn[k];
+        int p = ref_idx ? ref_idx[i] : path_index;
+        if (p >= 0 && p < pv.n_paths) {                                     // tracking' = T(x', y', phi', vx')
+            // the closest waypoint is an integer index (tf.argmin): the reference point is a constant
+            // of the derivative, so no waypoint scan is needed here
+            const float ex = nxt[3], ey = nxt[4];
+            float ddx = 0.f, ddy = 0.f;                                     // d(two2one)/d(ex, ey) = -d(delta)
+            if (task == 0) {
+                const float rho = __fsqrt_rn(sq(ex + CE2E_HALF) + sq(ey + CE2E_HALF));
+                ddx = -(ex + CE2E_HALF) / rho; ddy = -(ey + CE2E_HALF) / rho;
+                if (ey < -CE2E_HALF) { ddx = -1.0f; ddy = 0.0f; }
+                if (ex < -CE2E_HALF) { ddx = 0.0f; ddy = -1.0f; }
+            } else if (task == 1) {
+                ddx = -1.0f;
+            } else {
+                const float rho = __fsqrt_rn(sq(ex - CE2E_HALF) + sq(ey + CE2E_HALF));
+                ddx = (ex - CE2E_HALF) / rho; ddy = (ey + CE2E_HALF) / rho;
+                if (ey < -CE2E_HALF) { ddx = -1.0f; ddy = 0.0f; }
+                if (ex > CE2E_HALF) { ddx = 0.0f; ddy = 1.0f; }
+            }
+            g_n[3] += gn[6] * ddx;
+            g_n[4] += gn[6] * ddy;
+            g_n[5] += gn[7];
+            g_n[0] += gn[8];
+            for (int k = 0; k < n_future; ++k) {                             // (fx - x', fy - y', wrap(phi' - fphi))
+                g_n[3] -= gn[9 + 3 * k];
+                g_n[4] -= gn[10 + 3 * k];
+                g_n[5] += gn[11 + 3 * k];
+            }
+        }
+        if (!(vx_raw >= 0.0f && vx_raw <= 35.0f)) g_n[0] = 0.0f;            // clip_by_value (DM:390)
+        // ---- back through f_xu (DM:73-81)
+        {
+            const float tau = K.tau;
+            // vx' = vx + tau (a_x + vy r)
+            gvx += g_n[0]; gvy += g_n[0] * tau * r; gr += g_n[0] * tau * vy; gax += g_n[0] * tau;
+            // vy' = N1 / D1
+            const float D1 = K.m * vx - K.Dv, vy1 = nxt[1];
+            const float k1 = g_n[1] / D1;
+            gvx += k1 * ((K.m * vy - K.tauCf * steer - 2.0f * K.taum * vx * r) - vy1 * K.m);
+            gvy += k1 * (K.m * vx);
+            gr += k1 * (K.tauK1 - K.taum * vx * vx);
+            gsteer += k1 * (-K.tauCf * vx);
+            // r' = N2 / D2
+            const float D2 = K.Dr - K.Iz * vx, r1 = nxt[2];
+            const float k2 = g_n[2] / D2;
+            gvx += k2 * ((-K.Iz * r + K.tauaCf * steer) + r1 * K.Iz);
+            gvy += k2 * (-K.tauK1);
+            gr += k2 * (-K.Iz * vx);
+            gsteer += k2 * (K.tauaCf * vx);
+            // x' = x + tau (vx c - vy s), y' = y + tau (vx s + vy c)
+            gx += g_n[3]; gy += g_n[4];
+            gvx += tau * (g_n[3] * c + g_n[4] * s);
+            gvy += tau * (-g_n[3] * s + g_n[4] * c);
+            gphi += D2R * tau * (g_n[3] * (-vx * s - vy * c) + g_n[4] * (vx * c - vy * s));
+            // phi' = phi + tau r 180/pi
+            gphi += g_n[5];
+            gr += g_n[5] * tau * (180.0f / CE2E_PI32);
+        }
+    }
+    if (TILED) {
+        gvx += __shfl_xor_sync(0xffffffffu, gvx, 1);
+        gvy += __shfl_xor_sync(0xffffffffu, gvy, 1);
+        gr += __shfl_xor_sync(0xffffffffu, gr, 1);
+        gx += __shfl_xor_sync(0xffffffffu, gx, 1);
+        gy += __shfl_xor_sync(0xffffffffu, gy, 1);
+        gphi += __shfl_xor_sync(0xffffffffu, gphi, 1);
+        gsteer += __shfl_xor_sync(0xffffffffu, gsteer, 1);
+        gax += __shfl_xor_sync(0xffffffffu, gax, 1);
+        if (!owner) return;
     }
     float *go = g_obs + i * ld_go;
     go[0] = gvx; go[1] = gvy; go[2] = gr; go[3] = gx; go[4] = gy; go[5] = gphi;
@@ -1551,9 +1635,16 @@ int ce2e_rollout_step_backward(const ce2e_paths *paths, int path_index, const in
         return fail(CE2E_ERR_SHAPE, "bad V / n_future / ld");
     if (!ref_idx && (path_index < 0 || path_index >= paths->n_paths))
         return fail(CE2E_ERR_PATH, "path_index %d outside [0, %d)", path_index, paths->n_paths);
-    k_model_step_bwd<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
-        make_view(paths), make_grid_view(paths), make_dyn_consts(1.0 / 10.0), paths->task, path_index, ref_idx,
-        obs_in, ld_in, act_norm, V_in, n_future, g_next, ld_gnext, g_out5, g_obs, ld_gobs, g_act, B);
+    if (aligned16(obs_in + n_cols) && ld_in % 4 == 0 && V_in > 0) {
+        const int64_t n_tiles = (B + RPW - 1) / RPW;
+        k_model_step_bwd<true><<<blocks_for(n_tiles, BWD_WARPS), BWD_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            make_view(paths), make_grid_view(paths), make_dyn_consts(1.0 / 10.0), paths->task, path_index, ref_idx,
+            obs_in, ld_in, act_norm, V_in, n_future, g_next, ld_gnext, g_out5, g_obs, ld_gobs, g_act, B);
+    } else {
+        k_model_step_bwd<false><<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
+            make_view(paths), make_grid_view(paths), make_dyn_consts(1.0 / 10.0), paths->task, path_index, ref_idx,
+            obs_in, ld_in, act_norm, V_in, n_future, g_next, ld_gnext, g_out5, g_obs, ld_gobs, g_act, B);
+    }
     return after_launch("k_model_step_bwd");
 }
 

@@ -105,3 +105,41 @@ def test_no_grad_path_unchanged(dm):
     for p, d in zip(plain, diff):
         assert np.array_equal(p.view(np.int32), d.detach().cpu().numpy().view(np.int32))
     assert diff[1].requires_grad and diff[0].requires_grad
+
+
+@pytest.mark.parametrize('V', [1, 5, 8, 32, 37])
+def test_backward_tiled_equals_scalar(dm, V):
+    """ce2e_rollout_step_backward has two kernels: rows with a 16 B aligned vehicle block take the tiled
+    one (two lanes per row, vehicles staged through shared memory), anything else the scalar one.  Same
+    gradients up to the summation order of the collision terms (two halves vs. one running sum)."""
+    import ctypes
+    from env_build_b200 import _lib, synthetic as syn
+    rng = np.random.default_rng(100 + V)
+    task, B = 'right', 1501                                     # ragged: last tile has 13 rows
+    model = dm.EnvironmentModel(task, mode='training', veh_mode_list=syn.tiled_mode_list(orc.VEHICLE_MODE_LIST[task], V))
+    ref = syn.make_ref_indexes(rng, B, out_of_range_frac=0.03)
+    obs = syn.make_obs(rng, B, task, V, model.ref_path.path_list, ref)
+    D = obs.shape[1]
+    act = torch.as_tensor(syn.make_actions(rng, 1, B)[0], device='cuda')
+    dref = torch.as_tensor(ref, device='cuda', dtype=torch.int32)
+    g_next = torch.randn((B, 9), device='cuda')
+    g_out5 = torch.randn((5, B), device='cuda')
+    lib, vp = _lib.load(), (lambda t: ctypes.c_void_p(t.data_ptr()))
+    got = []
+    for padded in (True, False):
+        if padded:
+            o = dm.padded_rows(B, D, 9, torch.device('cuda'))
+            o.copy_(torch.as_tensor(obs))
+            assert (o.data_ptr() + 36) % 16 == 0 and o.stride(0) % 4 == 0
+        else:
+            o = torch.as_tensor(obs, device='cuda').contiguous()
+            assert o.stride(0) % 4 != 0 or (o.data_ptr() + 36) % 16 != 0
+        g_obs = torch.full((B, 9), float('nan'), device='cuda')
+        g_act = torch.full((B, 2), float('nan'), device='cuda')
+        _lib.check(lib.ce2e_rollout_step_backward(model.ref_path.handle, 0, vp(dref), vp(o), o.stride(0), vp(act), V, 0,
+                                                  vp(g_next), 9, vp(g_out5), vp(g_obs), 9, vp(g_act), B, None))
+        torch.cuda.synchronize()
+        got.append((g_obs.cpu().numpy(), g_act.cpu().numpy()))
+    for a, b in zip(got[0], got[1]):
+        assert np.isfinite(a).all() and np.isfinite(b).all()
+        assert np.allclose(a, b, rtol=1e-4, atol=1e-4), float(np.abs(a - b).max())
