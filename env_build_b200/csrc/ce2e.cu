@@ -180,7 +180,10 @@ struct StepParams {
     int64_t ld_in, ld_out, B;
     int task, path_index, V_in, V_out, n_future, flags;
     int horizon;                 // FUSED kernels: steps per launch (act = tape [H,B,2], out5 = [H,5,B])
-    ce2e_turn_classes turn;
+    // per-vehicle turn tables derived from ce2e_turn_classes (DM:416-421): signed arc radius
+    // (+26.875 left-turn modes, -15.625 right-turn modes), its rounded reciprocal, and the half
+    // width of the box inside which the heading turns (25, or -1 = never for straight modes)
+    float turn_rs[CE2E_MAX_VEH], turn_rr[CE2E_MAX_VEH], turn_half[CE2E_MAX_VEH];
 };
 
 constexpr int STEP_WARPS = 14;           // two 448-thread blocks per SM = 28 warps (<= 72 registers)
@@ -238,8 +241,27 @@ __device__ __forceinline__ void pair_gate(float ex, float ey, float px, float py
 
 // One surrounding vehicle of one row: gate its four circle pairs against the ego circles and
 // return its predicted state (DM:218-229, DM:405-427).  Branch free.
+// predict_for_a_mode (DM:405-427) with the turn class folded into per-vehicle constants: the
+// signed division reproduces -(v/R)/10 exactly ((-q) and q round alike), half = -1 disables the arc.
+__device__ __forceinline__ float4 veh_predict_tab(float4 v, float th, float s, float c, float rs, float rr,
+                                                  float half) {
+    const float step = div10(v.z);
+    float4 n;
+    n.x = v.x + step * c;
+    n.y = v.y + step * s;
+    n.z = v.z;
+    const bool inside = (fabsf(v.x) < half) && (fabsf(v.y) < half);
+    const float q = div10(div_const(v.z, rs, rr));
+    float t2 = th + (inside ? q : 0.0f);
+    t2 = (t2 > CE2E_PI32) ? t2 - CE2E_TWO_PI32 : t2;
+    t2 = (t2 <= -CE2E_PI32) ? t2 + CE2E_TWO_PI32 : t2;
+    n.w = rad2deg(t2);
+    return n;
+}
+
 template <bool REW, bool NEXT, bool FAST>
-__device__ __forceinline__ float4 vehicle_step(float4 v, const Circles &ec, int tc, unsigned &qa) {
+__device__ __forceinline__ float4 vehicle_step(float4 v, const Circles &ec, float rs, float rr, float half,
+                                               unsigned &qa) {
     const float th = deg2rad(v.w);
     float vs, vc;
     if (FAST) sincos_mufu(th, vs, vc);
@@ -251,7 +273,7 @@ __device__ __forceinline__ float4 vehicle_step(float4 v, const Circles &ec, int 
         pair_gate(ec.rx, ec.ry, w.fx, w.fy, qa);
         pair_gate(ec.rx, ec.ry, w.rx, w.ry, qa);
     }
-    return NEXT ? veh_predict_one(v, th, vs, vc, tc) : v;
+    return NEXT ? veh_predict_tab(v, th, vs, vc, rs, rr, half) : v;
 }
 
 // The nearest-waypoint candidate range of (x, y) on path p: the grid cell's [lo, hi] widened to
@@ -518,14 +540,14 @@ k_model_step(const __grid_constant__ StepParams P) {
 #pragma unroll
                 for (int e = 0; e < VPL; e += 2) {          // two independent vehicles at a time
                     float4 v0 = slot[e ^ swz], v1 = slot[(e + 1) ^ swz];
-                    v0 = vehicle_step<REW, NEXT, FAST>(v0, ec, P.turn.tc[j0 + e], qa);
-                    v1 = vehicle_step<REW, NEXT, FAST>(v1, ec, P.turn.tc[j0 + e + 1], qa);
+                    v0 = vehicle_step<REW, NEXT, FAST>(v0, ec, P.turn_rs[j0 + e], P.turn_rr[j0 + e], P.turn_half[j0 + e], qa);
+                    v1 = vehicle_step<REW, NEXT, FAST>(v1, ec, P.turn_rs[j0 + e + 1], P.turn_rr[j0 + e + 1], P.turn_half[j0 + e + 1], qa);
                     if (NEXT) { slot[e ^ swz] = v0; slot[(e + 1) ^ swz] = v1; }
                 }
             } else {
                 for (int e = 0; e < VPL; ++e) {
                     if (j0 + e < j_end) {
-                        const float4 nv = vehicle_step<REW, NEXT, FAST>(slot[e ^ swz], ec, P.turn.tc[j0 + e], qa);
+                        const float4 nv = vehicle_step<REW, NEXT, FAST>(slot[e ^ swz], ec, P.turn_rs[j0 + e], P.turn_rr[j0 + e], P.turn_half[j0 + e], qa);
                         if (NEXT && j0 + e < P.V_out) slot[e ^ swz] = nv;
                     }
                 }
@@ -1345,7 +1367,12 @@ int model_step_common(const ce2e_paths *paths, int task, int path_index, const i
             return fail(CE2E_ERR_PATH, "path tables live on device %d, current device is %d", paths->device, cur_dev);
         P.pv = make_view(paths);
         P.gv = make_grid_view(paths);
-        if (turn) P.turn = *turn;
+        for (int j = 0; j < V_out; ++j) {
+            const int tc = turn ? turn->tc[j] : 0;
+            P.turn_rs[j] = tc > 0 ? CE2E_R_LEFT : (tc < 0 ? -CE2E_R_RIGHT : 1.0f);
+            P.turn_rr[j] = tc > 0 ? 1.0f / CE2E_R_LEFT : (tc < 0 ? -(1.0f / CE2E_R_RIGHT) : 0.0f);
+            P.turn_half[j] = tc != 0 ? CE2E_HALF : -1.0f;
+        }
     } else {
         P.pv.n_paths = 0;
         P.pv.stride = 0;
