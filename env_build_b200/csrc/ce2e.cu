@@ -206,18 +206,10 @@ typedef WarpScratchT<2> WarpScratch;
 __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async8(unsigned smem_dst, const void *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-// Block-wide named barrier, NON-aligned form: the warps of a block reach it from two different
-// places (inside their first tile, or after the tile loop when they own no tile).
-__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
-    asm volatile("barrier.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v));
@@ -323,15 +315,31 @@ k_model_step(const __grid_constant__ StepParams P) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool vec_in = P.flags & F_VEC_IN, vec_out = P.flags & F_VEC_OUT;
     bool tables_pending = false;
+    unsigned s_mbar = 0;
     if (NEXT) {
-        // path tables -> shared memory with 8 B async copies; they are static, so this may run
-        // before the previous launch has finished (programmatic dependent launch) and is only
-        // waited for right before the first waypoint scan
-        const int tot = P.pv.n_paths * P.pv.stride;           // stride is even: tot * 4 B is a multiple of 8
+        // path tables -> shared memory with two bulk copies issued by one thread and tracked by an
+        // mbarrier; they are static, so this may run before the previous launch has finished
+        // (programmatic dependent launch); a warp polls the mbarrier right before its first
+        // waypoint scan, without meeting the other warps of the block
+        const int tot = P.pv.n_paths * P.pv.stride;           // stride is even: tot * 8 B is a multiple of 16
+        const int tot4 = (tot + 3) & ~3;                      // the phi table is padded to 16 B
         const unsigned sx = (unsigned)__cvta_generic_to_shared(s_xy), sp = (unsigned)__cvta_generic_to_shared(s_phi);
-        for (int i = tid; i < tot; i += STEP_THREADS) cp_async8(sx + 8u * i, P.pv.xy + i);
-        for (int i = tid; i < tot / 2; i += STEP_THREADS) cp_async8(sp + 8u * i, P.pv.phi + 2 * i);
-        cp_async_commit();
+        s_mbar = sp + 4u * tot4;
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(s_mbar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s_mbar), "r"(12u * tot4 - 8u * (tot4 - tot))
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(sx),
+                         "l"(P.pv.xy), "r"(8u * tot), "r"(s_mbar)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(sp),
+                         "l"(P.pv.phi), "r"(4u * tot4), "r"(s_mbar)
+                         : "memory");
+        }
         tables_pending = true;
     }
     // everything below reads what the previous launch of a rollout wrote
@@ -421,10 +429,13 @@ k_model_step(const __grid_constant__ StepParams P) {
         float s, c;
         sincos_cw(phi, s, c);
         const Circles ec = circle_centres(x, y, s, c);
-        if (tables_pending) {                 // first tile of this warp: the path tables must have
-            cp_async_wait<1>();               // landed (the vehicle chunk staged above may still fly)
+        if (tables_pending) {                 // first tile of this warp: the path tables must have landed
+            unsigned done;
+            do {
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
+                             : "=r"(done) : "r"(s_mbar) : "memory");
+            } while (!done);
             tables_pending = false;
-            named_barrier_sync(1, STEP_THREADS);
         }
 
         float rewards = 0.f, v2r_tr = 0.f, v2r_re = 0.f;
@@ -607,10 +618,6 @@ k_model_step(const __grid_constant__ StepParams P) {
         }
         }                                         // step loop
     }
-    if (tables_pending) {                     // a warp without tiles still owes the block its arrival
-        cp_async_wait<0>();
-        named_barrier_sync(1, STEP_THREADS);
-    }
 }
 
 GridView make_grid_view(const ce2e_paths *p) {
@@ -635,7 +642,7 @@ int launch_model_step(StepParams &P, cudaStream_t st) {
     if (P.ld_in > (1 << 24) || P.ld_out > (1 << 24)) return fail(CE2E_ERR_SHAPE, "row stride too large");
     const int64_t n_tiles = (P.B + RPW - 1) / RPW;
     const bool fused = P.horizon > 0;
-    size_t smem = (size_t)P.pv.n_paths * P.pv.stride * 12 +
+    size_t smem = (size_t)P.pv.n_paths * P.pv.stride * 12 + 32 +
                   STEP_WARPS * (fused ? sizeof(WarpScratchT<FUSED_MAX_CHUNKS>) : sizeof(WarpScratch));
     if ((int)smem > di->max_smem_optin)
         return fail(CE2E_ERR_SHAPE, "path tables need %zu B of shared memory (max %d)", smem,
@@ -1431,7 +1438,7 @@ int ce2e_paths_create(int task, int n_paths, const int32_t *lens, const float *c
     h->stride10 = stride;
     cudaGetDevice(&h->device);
     std::vector<float2> xy((size_t)n_paths * stride, make_float2(1e30f, 1e30f));
-    std::vector<float> ph((size_t)n_paths * stride, 0.f);
+    std::vector<float> ph((((size_t)n_paths * stride + 3) & ~(size_t)3), 0.f);   // padded to 16 B (bulk copy)
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < n_paths && e == cudaSuccess; ++i) {
         const int L = lens[i];
