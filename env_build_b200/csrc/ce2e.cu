@@ -401,11 +401,6 @@ k_model_step(const __grid_constant__ StepParams P) {
             }
             cp_async_commit();
         };
-        if (FUSED) {
-            for (int ch = 0; ch < n_chunks; ++ch) stage(ch, ch);      // the whole row, once
-        } else if (n_chunks > 0) {
-            stage(0, 0);
-        }
         // ---------------- ego phase ----------------
         float e9[9];
         if (vec_in && veh_off == 9) {           // o[1] is 16 B aligned: 1 scalar + 2 vector loads
@@ -418,12 +413,18 @@ k_model_step(const __grid_constant__ StepParams P) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) e9[i] = o[i];
         }
+        const float act0_pre = P.act[2 * rr], act1_pre = P.act[2 * rr + 1];
+        if (FUSED) {
+            for (int ch = 0; ch < n_chunks; ++ch) stage(ch, ch);      // the whole row, once
+        } else if (n_chunks > 0) {
+            stage(0, 0);
+        }
         const int n_steps = FUSED ? P.horizon : 1;
         for (int step = 0; step < n_steps; ++step) {
         const float *act_t = P.act + (FUSED ? (int64_t)step * 2 * P.B : 0);
         const bool last_step = !FUSED || step == n_steps - 1;
         const float vx = e9[0], vy = e9[1], r = e9[2], x = e9[3], y = e9[4], phi_deg = e9[5];
-        float steer = act_t[2 * rr], a_x = act_t[2 * rr + 1];
+        float steer = (FUSED && step > 0) ? act_t[2 * rr] : act0_pre, a_x = (FUSED && step > 0) ? act_t[2 * rr + 1] : act1_pre;
         if (P.flags & F_ACT_NORM) action_transform(steer, a_x, steer, a_x);
         const float phi = deg2rad(phi_deg);
         float s, c;
@@ -523,6 +524,7 @@ k_model_step(const __grid_constant__ StepParams P) {
         unsigned qa = q_lane;
         auto flush = [&]() {                      // finish this lane's queued pairs, in order
             const int cnt = (int)(qa - q_lane) >> 7;
+#pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
                 const float d = __fsqrt_rn(lds_f32(q_lane + (unsigned)i * 128u));
                 const float g35 = d - 3.5f, g25 = d - 2.5f;
