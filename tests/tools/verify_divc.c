@@ -15,9 +15,10 @@ static uint32_t to_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 int main(int argc, char **argv) {
     uint64_t stride = argc > 1 ? strtoull(argv[1], 0, 10) : 1;
     const float PI32 = 3.14159274101257324f;
-    const float divisors[5] = {180.0f, PI32, 10.0f, 26.875f, 15.625f};
+    /* -15.625: the right-turn arc enters the kernel as a signed radius (x / -R == -(x / R)) */
+    const float divisors[6] = {180.0f, PI32, 10.0f, 26.875f, 15.625f, -15.625f};
     int bad = 0;
-    for (int d = 0; d < 5; ++d) {
+    for (int d = 0; d < 6; ++d) {
         const float c = divisors[d];
         const volatile float one = 1.0f;
         const float rc = one / c;
