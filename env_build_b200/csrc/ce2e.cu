@@ -873,6 +873,69 @@ __global__ void k_ss(const float *__restrict__ obs, int64_t ld, const float *__r
     out[i] = acc;
 }
 
+// ------------------------------------------------------------------------------------------
+// Vehicle stream of the small tiled kernels (k_env_done, k_model_step_bwd): k_model_step's
+// decomposition without its persistent loop.  A warp owns RPW = 16 consecutive rows, two lanes per
+// row; lane h visits half h of the row's vehicle list.  The 16 B vehicle records travel through
+// shared memory in chunks of VPL = 4 per lane with coalesced cp.async copies (piece k of a lane =
+// row (lane / 8) + 4 k of the tile, vehicle (lane % 4) of half (lane / 4) % 2; it lands in the slot
+// of lane 2 * row + half at float4 index vehicle ^ (row % 4)), double buffered.  Needs a 16 B
+// aligned vehicle block and ld % 4 == 0.
+// ------------------------------------------------------------------------------------------
+constexpr int TILED_WARPS = 8;
+struct VehicleStream {
+    float *buf;                // this warp's 2 x (32 * 4 * VPL) floats
+    const float *g_in;
+    int64_t ld;
+    int V, H, n_chunks, rows_here, lane, p_row, p_half, p_veh, p_soff;
+
+    __device__ __forceinline__ void init(float *warp_buf, const float *obs, int64_t ld_, int veh_off, int V_,
+                                         int64_t tile, int64_t B, int lane_) {
+        buf = warp_buf; ld = ld_; V = V_; lane = lane_;
+        H = (V + 1) >> 1;
+        n_chunks = (H + VPL - 1) / VPL;
+        rows_here = (int)min((int64_t)RPW, B - tile * RPW);
+        p_row = lane >> 3; p_half = (lane >> 2) & 1;
+        const int p_e = lane & 3;
+        p_veh = p_half * H + p_e;
+        p_soff = (2 * p_row + p_half) * (4 * VPL) + ((p_e ^ (p_row & 3)) << 2);
+        g_in = obs + tile * RPW * ld + (p_row * ld + veh_off + 4 * p_veh);
+    }
+    __device__ __forceinline__ void stage(int ch, int b) const {
+        constexpr int PIECE_STRIDE = 8 * 4 * VPL;
+        if (p_veh + ch * VPL < (p_half ? V : min(H, V))) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (p_row + 4 * k < rows_here)
+                    cp_async16((unsigned)__cvta_generic_to_shared(buf + b * (32 * 4 * VPL) + p_soff + k * PIECE_STRIDE),
+                               g_in + ch * (4 * VPL) + 4 * k * ld);
+        }
+        cp_async_commit();
+    }
+    __device__ __forceinline__ void begin() const {
+        if (n_chunks > 0) stage(0, 0);
+    }
+    // f(float4 vehicle) for every vehicle of this lane's half, in list order; begin() came first
+    template <class F>
+    __device__ __forceinline__ void run(F &&f) const {
+        const int h = lane & 1, swz = (lane >> 1) & 3;
+        const int j_end = h ? V : min(H, V);
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            if (ch + 1 < n_chunks) stage(ch + 1, (ch + 1) & 1);
+            else cp_async_commit();
+            cp_async_wait<1>();
+            __syncwarp();
+            const float4 *slot = reinterpret_cast<const float4 *>(buf + (ch & 1) * (32 * 4 * VPL) + lane * (4 * VPL));
+            const int j0 = h * H + ch * VPL;
+#pragma unroll
+            for (int e = 0; e < VPL; ++e)
+                if (j0 + e < j_end) f(slot[e ^ swz]);
+            __syncwarp();
+        }
+        cp_async_wait<0>();
+    }
+};
+
 // CrossroadEnd2end._judge_done (E2E:200-256) on the observation AFTER a step, one thread per row.
 // Order of the checks as in the reference: collision (Traffic.collision_check, traffic.py:263-295,
 // with every surrounding vehicle taken as L x W = 4.8 x 2.0 like the ego), road constraint on the
@@ -889,11 +952,31 @@ __device__ __forceinline__ bool feasible_point(int task, float px, float py) {
     return (px > CE2E_LW2 && px < road && py <= -CE2E_HALF) || (py > -road && py < 0.f && px > CE2E_HALF);
 }
 
-__global__ void k_env_done(const __grid_constant__ DynConsts K, int task, const float *__restrict__ obs,
-                           int64_t ld, const float *__restrict__ act_scaled, int V, int veh_off,
-                           int v_light, int8_t *__restrict__ done, int64_t B) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B) return;
+// TILED = false: one thread per row, scalar loads (any alignment).  TILED = true: VehicleStream,
+// the collision test branch free (a quarter of the synthetic vehicles sit inside the 10 m gate, so a
+// branch would run for nearly every vehicle with a few live lanes), the two halves OR-ed by shuffle.
+template <bool TILED>
+__global__ void __launch_bounds__(TILED ? TILED_WARPS * 32 : 128)
+k_env_done(const __grid_constant__ DynConsts K, int task, const float *__restrict__ obs,
+           int64_t ld, const float *__restrict__ act_scaled, int V, int veh_off,
+           int v_light, int8_t *__restrict__ done, int64_t B) {
+    __shared__ __align__(16) float s_veh[TILED ? TILED_WARPS : 1][TILED ? 2 * 32 * 4 * VPL : 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = (int64_t)blockIdx.x * TILED_WARPS + warp;
+    int64_t i;
+    bool owner = true;
+    VehicleStream vs;
+    if (TILED) {
+        if (tile * RPW >= B) return;         // whole warp
+        const int64_t row = tile * RPW + (lane >> 1);
+        owner = row < B && (lane & 1) == 0;
+        i = row < B ? row : B - 1;
+        vs.init(s_veh[warp], obs, ld, veh_off, V, tile, B, lane);
+        vs.begin();
+    } else {
+        i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= B) return;
+    }
     const float *o = obs + i * ld;
     const float vx = o[0], r = o[2], x = o[3], y = o[4], phi = o[5], dy = o[6];
     float s, c;
@@ -904,14 +987,28 @@ __global__ void k_env_done(const __grid_constant__ DynConsts K, int task, const 
         const Circles e = circle_centres(x, y, s, c);
         const float thr = 6.25f;
         bool hit = false;
-        for (int j = 0; j < V; ++j) {
-            const float *v = o + veh_off + 4 * j;
-            if (fabsf(v[0] - x) < 10.0f && fabsf(v[1] - y) < 10.0f) {
-                float vs, vc;
-                sincos_cw(deg2rad(v[3]), vs, vc);
-                const Circles w = circle_centres(v[0], v[1], vs, vc);
-                hit = hit || (sq(e.fx - w.fx) + sq(e.fy - w.fy) < thr) || (sq(e.fx - w.rx) + sq(e.fy - w.ry) < thr) ||
-                      (sq(e.rx - w.rx) + sq(e.ry - w.ry) < thr) || (sq(e.rx - w.fx) + sq(e.ry - w.fy) < thr);
+        if (TILED) {
+            vs.run([&](float4 v) {
+                float ws, wc;
+                sincos_cw(deg2rad(v.w), ws, wc);
+                const Circles w = circle_centres(v.x, v.y, ws, wc);
+                const bool gate = fabsf(v.x - x) < 10.0f && fabsf(v.y - y) < 10.0f;
+                const bool in = (sq(e.fx - w.fx) + sq(e.fy - w.fy) < thr) | (sq(e.fx - w.rx) + sq(e.fy - w.ry) < thr) |
+                                (sq(e.rx - w.rx) + sq(e.ry - w.ry) < thr) | (sq(e.rx - w.fx) + sq(e.ry - w.fy) < thr);
+                hit |= gate & in;
+            });
+            hit |= (bool)__shfl_xor_sync(0xffffffffu, (int)hit, 1);
+            if (!owner) return;
+        } else {
+            for (int j = 0; j < V; ++j) {
+                const float *v = o + veh_off + 4 * j;
+                if (fabsf(v[0] - x) < 10.0f && fabsf(v[1] - y) < 10.0f) {
+                    float ws, wc;
+                    sincos_cw(deg2rad(v[3]), ws, wc);
+                    const Circles w = circle_centres(v[0], v[1], ws, wc);
+                    hit = hit || (sq(e.fx - w.fx) + sq(e.fy - w.fy) < thr) || (sq(e.fx - w.rx) + sq(e.fy - w.ry) < thr) ||
+                          (sq(e.rx - w.rx) + sq(e.ry - w.ry) < thr) || (sq(e.rx - w.fx) + sq(e.ry - w.fy) < thr);
+                }
             }
         }
         if (hit) code = 1;
@@ -1006,14 +1103,11 @@ __device__ __forceinline__ void pair_grad(float ex, float ey, float px, float py
 }
 
 // TILED = false: one thread per row, scalar loads (any alignment).
-// TILED = true : the forward's decomposition -- a warp owns 16 rows, two lanes per row; lane h sums
-//                the collision gradient over vehicle half h, the halves' 16 B vehicle records
-//                streamed through shared memory with coalesced cp.async copies (double buffered);
-//                then lane 0 takes the reward / road terms and lane 1 the next-observation terms.
-//                Needs a 16 B aligned vehicle block, ld % 4 == 0.
-constexpr int BWD_WARPS = 8;
+// TILED = true : VehicleStream -- a warp owns 16 rows, two lanes per row; lane h sums the collision
+//                gradient over vehicle half h; then lane 0 takes the reward / road terms and lane 1
+//                the next-observation terms.  Needs a 16 B aligned vehicle block, ld % 4 == 0.
 template <bool TILED>
-__global__ void __launch_bounds__(TILED ? BWD_WARPS * 32 : 128, TILED ? 4 : 1)
+__global__ void __launch_bounds__(TILED ? TILED_WARPS * 32 : 128, TILED ? 4 : 1)
 k_model_step_bwd(const __grid_constant__ PathView pv, const __grid_constant__ GridView gv,
                  const __grid_constant__ DynConsts K, int task, int path_index,
                  const int32_t *__restrict__ ref_idx, const float *__restrict__ obs,
@@ -1021,9 +1115,9 @@ k_model_step_bwd(const __grid_constant__ PathView pv, const __grid_constant__ Gr
                  const float *__restrict__ g_next, int64_t ld_gn,
                  const float *__restrict__ g_out5, float *__restrict__ g_obs, int64_t ld_go,
                  float *__restrict__ g_act, int64_t B) {
-    __shared__ __align__(16) float s_veh[TILED ? BWD_WARPS : 1][2][TILED ? 32 * 4 * VPL : 4];
+    __shared__ __align__(16) float s_veh[TILED ? TILED_WARPS : 1][TILED ? 2 * 32 * 4 * VPL : 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t tile = (int64_t)blockIdx.x * BWD_WARPS + warp;
+    const int64_t tile = (int64_t)blockIdx.x * TILED_WARPS + warp;
     int64_t i;
     bool owner = true;                       // this thread writes the row's outputs
     if (TILED) {
@@ -1037,27 +1131,11 @@ k_model_step_bwd(const __grid_constant__ PathView pv, const __grid_constant__ Gr
     }
     const float *o = obs + i * ld;
     const int n_trk = 3 * (n_future + 1);
-    // TILED staging geometry (that of k_model_step): piece k of a lane = row (lane / 8) + 4 k of the
-    // tile, vehicle (lane % 4) of half (lane / 4) % 2 of the chunk; it lands in the slot of lane
-    // 2 * row + half at float4 index vehicle ^ (row % 4)
-    const int H = (V + 1) >> 1, n_chunks = (H + VPL - 1) / VPL;
-    const int rows_here = TILED ? (int)min((int64_t)RPW, B - tile * RPW) : 0;
-    const int p_row = lane >> 3, p_half = (lane >> 2) & 1, p_e = lane & 3;
-    const int p_veh = p_half * H + p_e;
-    const int p_soff = (2 * p_row + p_half) * (4 * VPL) + ((p_e ^ (p_row & 3)) << 2);
-    constexpr int PIECE_STRIDE = 8 * 4 * VPL;
-    const float *g_in = obs + (TILED ? tile * RPW : 0) * ld + (p_row * ld + 6 + n_trk + 4 * p_veh);
-    auto stage = [&](int ch, int b) {
-        if (p_veh + ch * VPL < (p_half ? V : min(H, V))) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (p_row + 4 * k < rows_here)
-                    cp_async16((unsigned)__cvta_generic_to_shared(&s_veh[TILED ? warp : 0][b][TILED ? p_soff + k * PIECE_STRIDE : 0]),
-                               g_in + ch * (4 * VPL) + 4 * k * ld);
-        }
-        cp_async_commit();
-    };
-    if (TILED && n_chunks > 0) stage(0, 0);          // in flight while the ego columns arrive
+    VehicleStream vs;
+    if (TILED) {
+        vs.init(s_veh[warp], obs, ld, 6 + n_trk, V, tile, B, lane);
+        vs.begin();                                   // in flight while the ego columns arrive
+    }
     const float vx = o[0], vy = o[1], r = o[2], x = o[3], y = o[4], phi_deg = o[5];
     const float a0 = act_norm[2 * i], a1 = act_norm[2 * i + 1];
     float steer, a_x;
@@ -1101,25 +1179,7 @@ k_model_step_bwd(const __grid_constant__ PathView pv, const __grid_constant__ Gr
             pair_grad(ec.rx, ec.ry, w.rx, w.ry, w_tr, w_re_v, grx, gry);
         };
         if (TILED) {
-            const int h = lane & 1, swz = (lane >> 1) & 3;
-            const int j_end = h ? V : min(H, V);
-            for (int ch = 0; ch < n_chunks; ++ch) {
-                if (ch + 1 < n_chunks) stage(ch + 1, (ch + 1) & 1);
-                else cp_async_commit();
-                cp_async_wait<1>();
-                __syncwarp();
-                const float4 *slot = reinterpret_cast<const float4 *>(&s_veh[warp][ch & 1][lane * (4 * VPL)]);
-                const int j0 = h * H + ch * VPL;
-#pragma unroll
-                for (int e = 0; e < VPL; ++e) {
-                    if (j0 + e < j_end) {
-                        const float4 v = slot[e ^ swz];
-                        one_vehicle(v.x, v.y, v.w);
-                    }
-                }
-                __syncwarp();
-            }
-            cp_async_wait<0>();
+            vs.run([&](float4 v) { one_vehicle(v.x, v.y, v.w); });
             // the two halves of the row
             gfx += __shfl_xor_sync(0xffffffffu, gfx, 1);
             gfy += __shfl_xor_sync(0xffffffffu, gfy, 1);
@@ -1340,6 +1400,19 @@ int check_batch(int64_t B) {
 }
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int launch_env_done(int task, const float *obs, int64_t ld, const float *act_scaled, int V, int veh_off,
+                    int v_light, int8_t *done, int64_t B, cudaStream_t st) {
+    if (V > 0 && aligned16(obs + veh_off) && ld % 4 == 0) {
+        const int64_t n_tiles = (B + RPW - 1) / RPW;
+        k_env_done<true><<<blocks_for(n_tiles, TILED_WARPS), TILED_WARPS * 32, 0, st>>>(
+            make_dyn_consts(1.0 / 10.0), task, obs, ld, act_scaled, V, veh_off, v_light, done, B);
+    } else {
+        k_env_done<false><<<blocks_for(B, 128), 128, 0, st>>>(make_dyn_consts(1.0 / 10.0), task, obs, ld, act_scaled,
+                                                             V, veh_off, v_light, done, B);
+    }
+    return after_launch("k_env_done");
+}
 
 int model_step_common(const ce2e_paths *paths, int task, int path_index, const int32_t *ref_idx,
                       const float *obs_in, int64_t ld_in, const float *act,
@@ -1622,10 +1695,8 @@ int ce2e_env_step(const ce2e_paths *paths, const int32_t *ref_idx, const float *
                                obs_out, ld_out, out5, dict16, act_scaled_out, B,
                                F_REWARD | F_NEXT | F_ACT_NORM | F_GYM_EGO, stream);
     if (rc || B == 0) return rc;
-    k_env_done<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
-        make_dyn_consts(1.0 / 10.0), paths->task, obs_out, ld_out, act_scaled_out, V,
-        6 + 3 * (n_future + 1), v_light, done_out, B);
-    return after_launch("k_env_done");
+    return launch_env_done(paths->task, obs_out, ld_out, act_scaled_out, V, 6 + 3 * (n_future + 1), v_light, done_out,
+                           B, (cudaStream_t)stream);
 }
 
 int ce2e_judge_done(int task, const float *obs, int64_t ld, const float *act_scaled, int V, int n_future,
@@ -1637,9 +1708,8 @@ int ce2e_judge_done(int task, const float *obs, int64_t ld, const float *act_sca
     if (!obs || !act_scaled || !done_out) return fail(CE2E_ERR_NULL, "NULL argument");
     if (V < 0 || V > CE2E_MAX_VEH || n_future < 0 || ld < 6 + 3 * (n_future + 1) + 4 * V)
         return fail(CE2E_ERR_SHAPE, "bad V / n_future / ld");
-    k_env_done<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(
-        make_dyn_consts(1.0 / 10.0), task, obs, ld, act_scaled, V, 6 + 3 * (n_future + 1), v_light, done_out, B);
-    return after_launch("k_env_done");
+    return launch_env_done(task, obs, ld, act_scaled, V, 6 + 3 * (n_future + 1), v_light, done_out, B,
+                           (cudaStream_t)stream);
 }
 
 int ce2e_veh_predict(const float *veh_in, int64_t ld_in, const ce2e_turn_classes *turn, int V,
@@ -1673,7 +1743,7 @@ int ce2e_rollout_step_backward(const ce2e_paths *paths, int path_index, const in
         return fail(CE2E_ERR_PATH, "path_index %d outside [0, %d)", path_index, paths->n_paths);
     if (aligned16(obs_in + n_cols) && ld_in % 4 == 0 && V_in > 0) {
         const int64_t n_tiles = (B + RPW - 1) / RPW;
-        k_model_step_bwd<true><<<blocks_for(n_tiles, BWD_WARPS), BWD_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        k_model_step_bwd<true><<<blocks_for(n_tiles, TILED_WARPS), TILED_WARPS * 32, 0, (cudaStream_t)stream>>>(
             make_view(paths), make_grid_view(paths), make_dyn_consts(1.0 / 10.0), paths->task, path_index, ref_idx,
             obs_in, ld_in, act_norm, V_in, n_future, g_next, ld_gnext, g_out5, g_obs, ld_gobs, g_act, B);
     } else {

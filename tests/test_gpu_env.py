@@ -203,3 +203,33 @@ def test_vehicle_selection(e2e, task):
     ex, ey = one.obs.numpy()[0, 3:5]
     want = orc.select_interested_vehicles(veh[0][cls[0] >= 0], cls[0][cls[0] >= 0], ex, ey, task)
     assert np.array_equal(one._construct_veh_vector_short().view(np.int32), want.view(np.int32))
+
+
+@pytest.mark.parametrize('V', [1, 5, 9, 32, 37])
+def test_judge_done_tiled_equals_scalar(e2e, V):
+    """ce2e_judge_done has two kernels (16 B aligned vehicle block -> tiled, else one thread per row);
+    the done codes are integers: identical."""
+    import ctypes
+    from env_build_b200 import _lib, synthetic as syn
+    from env_build_b200.dynamics_and_models import padded_rows, build_path_tables
+    rng = np.random.default_rng(200 + V)
+    task, B = 'left', 2093                                       # ragged: last tile has 13 rows
+    paths = build_path_tables(task)[0]
+    obs = craft(syn.make_obs(rng, B, task, V, paths, syn.make_ref_indexes(rng, B)), task, paths)
+    D = obs.shape[1]
+    sc = torch.as_tensor(rng.uniform(-3, 1.5, (B, 2)).astype(np.float32), device='cuda')
+    lib, vp = _lib.load(), (lambda t: ctypes.c_void_p(t.data_ptr()))
+    codes = []
+    for padded in (True, False):
+        if padded:
+            o = padded_rows(B, D, 9, torch.device('cuda'))
+            o.copy_(torch.as_tensor(obs))
+        else:
+            o = torch.as_tensor(obs, device='cuda').contiguous()
+            assert o.stride(0) % 4 != 0 or (o.data_ptr() + 36) % 16 != 0
+        done = torch.full((B,), -1, dtype=torch.int8, device='cuda')
+        _lib.check(lib.ce2e_judge_done(0, vp(o), o.stride(0), vp(sc), V, 0, 0, vp(done), B, None))
+        torch.cuda.synchronize()
+        codes.append(done.cpu().numpy())
+    assert (codes[0] >= 0).all() and (codes[0] == codes[1]).all()
+    assert (codes[0] == 1).sum() > 0 or V < 5                    # collisions present

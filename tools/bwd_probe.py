@@ -46,3 +46,8 @@ for V in (32, 8):
     bwd = lambda: _lib.check(lib.ce2e_rollout_step_backward(h, 0, vp(dref), vp(obs), obs.stride(0), vp(act), V, 0, vp(g_next), 9,
                                                             vp(g_out5), vp(g_obs), 9, vp(g_act), B, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     print('V=%d  forward %.1f us  backward %.1f us' % (V, t_us(fwd), t_us(bwd)))
+    done = torch.empty((B,), dtype=torch.int8, device='cuda')
+    sc = torch.zeros((B, 2), device='cuda')
+    jd = lambda: _lib.check(lib.ce2e_judge_done(0, vp(nxt), nxt.stride(0), vp(sc), V, 0, 0, vp(done), B,
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    print('V=%d  judge_done %.1f us' % (V, t_us(jd)))
