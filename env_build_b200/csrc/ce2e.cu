@@ -211,6 +211,28 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+// mbarrier + 1-D bulk async copy (the TMA path without a tensor map): one thread arms the barrier
+// with the byte count and issues the copies; any thread may then poll the phase.
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(unsigned smem_dst, const void *gsrc, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
+                 "l"(gsrc), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned mbar, unsigned parity) {
+    unsigned done;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(mbar), "r"(parity)
+                 : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(addr), "f"(v));
 }
@@ -325,20 +347,12 @@ k_model_step(const __grid_constant__ StepParams P) {
         const int tot4 = (tot + 3) & ~3;                      // the phi table is padded to 16 B
         const unsigned sx = (unsigned)__cvta_generic_to_shared(s_xy), sp = (unsigned)__cvta_generic_to_shared(s_phi);
         s_mbar = sp + 4u * tot4;
-        if (tid == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(s_mbar) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        }
+        if (tid == 0) mbar_init(s_mbar, 1);
         __syncthreads();
         if (tid == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s_mbar), "r"(12u * tot4 - 8u * (tot4 - tot))
-                         : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(sx),
-                         "l"(P.pv.xy), "r"(8u * tot), "r"(s_mbar)
-                         : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(sp),
-                         "l"(P.pv.phi), "r"(4u * tot4), "r"(s_mbar)
-                         : "memory");
+            mbar_expect_tx(s_mbar, 8u * tot + 4u * tot4);
+            bulk_copy_g2s(sx, P.pv.xy, 8u * tot, s_mbar);
+            bulk_copy_g2s(sp, P.pv.phi, 4u * tot4, s_mbar);
         }
         tables_pending = true;
     }
@@ -431,11 +445,7 @@ k_model_step(const __grid_constant__ StepParams P) {
         sincos_cw(phi, s, c);
         const Circles ec = circle_centres(x, y, s, c);
         if (tables_pending) {                 // first tile of this warp: the path tables must have landed
-            unsigned done;
-            do {
-                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}\n"
-                             : "=r"(done) : "r"(s_mbar) : "memory");
-            } while (!done);
+            while (!mbar_try_wait(s_mbar, 0)) {}
             tables_pending = false;
         }
 
