@@ -18,6 +18,7 @@
 #include "ce2e_device.cuh"
 #include "ce2e_grid.h"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -667,14 +668,16 @@ int launch_model_step(StepParams &P, cudaStream_t st) {
     else if (rew && next) kern = k_model_step<true, true>;
     else if (rew) kern = k_model_step<true, false>;
     else kern = k_model_step<false, true>;
-    // the opt-in shared-memory size is a per-device attribute of each kernel instantiation
-    static thread_local size_t smem_set[64][5] = {};
+    // the opt-in shared-memory size is a process-wide, per-device attribute of each kernel
+    // instantiation: raise it once to the device maximum (never to this call's size -- another host
+    // thread launching with larger path tables must not find it lowered)
+    static std::atomic<bool> smem_set[64][5];
     int dev = 0;
     CE2E_CUDA(cudaGetDevice(&dev));
-    size_t &set = smem_set[dev & 63][fused ? 4 : fast ? 3 : rew && next ? 0 : rew ? 1 : 2];
-    if (smem > set) {
-        CE2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        set = smem;
+    std::atomic<bool> &set = smem_set[dev & 63][fused ? 4 : fast ? 3 : rew && next ? 0 : rew ? 1 : 2];
+    if (!set.load(std::memory_order_acquire)) {
+        CE2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di->max_smem_optin));
+        set.store(true, std::memory_order_release);
     }
     // two persistent blocks per SM (one in the horizon-fused mode); never more blocks than tiles
     const int64_t max_blocks = (fused ? 1 : 2) * (int64_t)di->sms;

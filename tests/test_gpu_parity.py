@@ -675,3 +675,54 @@ def test_closed_loop_policy_in_graph(dm):
         cur = res[0].numpy()
     with pytest.raises(ValueError):
         RolloutGraph(model, B, V, H, fused=True, policy=policy)
+
+
+def test_reentrant_from_two_threads_and_streams(dm):
+    """include/ce2e.h: entry points are re-entrant, work goes to the caller's stream.  Two host threads,
+    each with its own stream, model and task, step concurrently; each must reproduce its own
+    single-threaded results bit for bit."""
+    import threading
+    from env_build_b200 import synthetic as syn
+    jobs = []
+    for k, (task, V) in enumerate((('left', 32), ('right', 9))):
+        rng = np.random.default_rng(900 + k)
+        B = 20000 + 17 * k
+        model = dm.EnvironmentModel(task, mode='training', veh_mode_list=tiled(task, V))
+        ref = syn.make_ref_indexes(rng, B)
+        obs = syn.make_obs(rng, B, task, V, model.ref_path.path_list, ref)
+        tape = syn.make_actions(rng, 12, B)
+        model.ref_path.handle                                   # tables built up front
+        jobs.append(dict(model=model, obs=obs, ref=ref, tape=tape))
+
+    def rollout(job, stream):
+        with torch.cuda.stream(stream):
+            m = job['model']
+            m.reset(job['obs'], job['ref'])
+            acc = 0
+            for t in range(len(job['tape'])):
+                res = m.rollout_out(job['tape'][t])
+                acc = acc + torch.stack([r.clone() for r in res[1:]])
+            out = (res[0].clone(), acc)
+        stream.synchronize()
+        return out
+
+    want = [rollout(j, torch.cuda.Stream()) for j in jobs]
+    got = [None, None]
+    errs = []
+
+    def worker(k):
+        try:
+            torch.cuda.set_device(0)
+            for _ in range(3):
+                got[k] = rollout(jobs[k], torch.cuda.Stream())
+        except Exception as e:                                  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for g, w in zip(got, want):
+        assert torch.equal(g[0], w[0]) and torch.equal(g[1], w[1])
