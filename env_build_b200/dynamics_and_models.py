@@ -226,7 +226,7 @@ class ReferencePath(object):
             self.path_list = [tuple(np.ascontiguousarray(a, dtype=np.float32) for a in p) for p in path_list]
             self.path_len_list, self.control_points = [], []
         self.ref_index = np.random.choice(len(self.path_list)) if ref_index is None else ref_index
-        self._handle = None
+        self._handles = {}                    # CUDA device ordinal -> ce2e_paths handle
 
     # -- path selection -------------------------------------------------------------------
     @property
@@ -248,7 +248,10 @@ class ReferencePath(object):
     # -- device tables --------------------------------------------------------------------
     @property
     def handle(self):
-        if self._handle is None:
+        """The device-resident tables on the CURRENT CUDA device (created on first use, one per device)."""
+        dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+        h = self._handles.get(dev)
+        if h is None:
             _device()
             n = len(self.path_list)
             if n > _lib.MAX_PATHS:
@@ -260,13 +263,13 @@ class ReferencePath(object):
             h = ctypes.c_void_p()
             _lib.check(_lib.load().ce2e_paths_create(_lib.TASK_ID[self.task], n, lens, cols[0], cols[1], cols[2],
                                                      ctypes.byref(h)))
-            self._handle = h
-        return self._handle
+            self._handles[dev] = h
+        return h
 
     def close(self):
-        if getattr(self, '_handle', None) is not None:
-            _lib.load().ce2e_paths_destroy(self._handle)
-            self._handle = None
+        handles, self._handles = getattr(self, '_handles', {}), {}
+        for h in handles.values():
+            _lib.load().ce2e_paths_destroy(h)
 
     def __del__(self):
         try:

@@ -59,3 +59,29 @@ def test_sharded_rollout_nccl(tmp_path, B):
     mp.spawn(_worker, args=(world, port, B, out), nprocs=world, join=True)
     got, want = np.load(out)
     assert got.shape == (B, 5) and np.array_equal(got.view(np.int32), want.view(np.int32))
+
+
+def test_one_process_two_devices():
+    """One process driving two GPUs: the same EnvironmentModel / ReferencePath objects keep one table
+    handle per device, inputs follow the current device; results are bit-identical on both."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip('needs >= 2 GPUs')
+    from env_build_b200 import synthetic as syn
+    from env_build_b200.dynamics_and_models import EnvironmentModel
+    rng = np.random.default_rng(12)
+    task, B, V = 'left', 3001, 8
+    model = EnvironmentModel(task, mode='training')
+    ref = syn.make_ref_indexes(rng, B)
+    obs = syn.make_obs(rng, B, task, V, model.ref_path.path_list, ref)
+    tape = syn.make_actions(rng, 3, B)
+    outs = []
+    for d in (0, 1, 0):
+        with torch.cuda.device(d):
+            model.reset(obs, ref)
+            for t in range(3):
+                res = model.rollout_out(tape[t])
+            assert res[0].device.index == d
+            outs.append([r.numpy() for r in res])
+    assert len(model.ref_path._handles) == 2
+    for a, b, c in zip(*outs):
+        assert np.array_equal(a.view(np.int32), b.view(np.int32)) and np.array_equal(a.view(np.int32), c.view(np.int32))
