@@ -8,6 +8,8 @@ allclose(rtol=1e-5, atol=1e-5) -- the tolerance BASELINE.json's north_star state
 Rows whose nearest-waypoint decision is a near-tie in the oracle (margin between the best and
 second-best squared distance < 1e-4 m^2) are excluded from next-obs tracking comparisons: a
 1-ulp difference in sin/cos can legitimately move such a row to the neighbouring waypoint."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -726,3 +728,61 @@ def test_reentrant_from_two_threads_and_streams(dm):
     assert not errs, errs
     for g, w in zip(got, want):
         assert torch.equal(g[0], w[0]) and torch.equal(g[1], w[1])
+
+
+def test_graph_capture_without_warmup(tmp_path):
+    """include/ce2e.h: every call is CUDA-graph capturable.  A fresh process captures the fused step, the
+    done kernel and the backward kernel in one graph WITHOUT calling them first (only the synchronous
+    ce2e_paths_create ran), replays it and compares with the eager results."""
+    import subprocess
+    import sys
+    script = tmp_path / 'capture.py'
+    script.write_text('''
+import ctypes, sys
+import numpy as np, torch
+sys.path.insert(0, %r)
+from env_build_b200 import _lib, synthetic as syn
+from env_build_b200.dynamics_and_models import EnvironmentModel, padded_rows
+rng = np.random.default_rng(1)
+task, B, V = 'left', 5000, 8
+m = EnvironmentModel(task, mode='training')
+ref = syn.make_ref_indexes(rng, B)
+obs_h = syn.make_obs(rng, B, task, V, m.ref_path.path_list, ref)
+dev = torch.device('cuda')
+obs = padded_rows(B, 41, 9, dev); obs.copy_(torch.as_tensor(obs_h))
+act = torch.as_tensor(syn.make_actions(rng, 1, B)[0], device=dev)
+dref = torch.as_tensor(ref, device=dev, dtype=torch.int32)
+lib, vp = _lib.load(), (lambda t: ctypes.c_void_p(t.data_ptr()))
+h = m.ref_path.handle                                  # synchronous setup, outside the capture
+
+def run(stream):
+    nxt = padded_rows(B, 41, 9, dev); out5 = torch.empty((5, B), device=dev); sc = torch.empty((B, 2), device=dev)
+    done = torch.empty((B,), dtype=torch.int8, device=dev)
+    g_obs = torch.empty((B, 9), device=dev); g_act = torch.empty((B, 2), device=dev)
+    ones9 = torch.ones((B, 9), device=dev); ones5 = torch.ones((5, B), device=dev)
+    def enqueue():
+        s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.ce2e_rollout_step(h, 0, vp(dref), vp(obs), obs.stride(0), vp(act), ctypes.byref(m._turn), V, V, 0,
+                                         vp(nxt), nxt.stride(0), vp(out5), vp(sc), B, s))
+        _lib.check(lib.ce2e_judge_done(0, vp(nxt), nxt.stride(0), vp(sc), V, 0, 0, vp(done), B, s))
+        _lib.check(lib.ce2e_rollout_step_backward(h, 0, vp(dref), vp(obs), obs.stride(0), vp(act), V, 0, vp(ones9), 9,
+                                                  vp(ones5), vp(g_obs), 9, vp(g_act), B, s))
+    return enqueue, (nxt, out5, done, g_obs, g_act)
+
+enq, outs = run(None)
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    enq()
+g.replay()
+torch.cuda.synchronize()
+captured = [o.clone() for o in outs]
+enq2, outs2 = run(None)
+enq2()
+torch.cuda.synchronize()
+for a, b in zip(captured, outs2):
+    assert torch.equal(a, b)
+assert int((captured[2] != 0).sum()) > 0
+print('CAPTURE OK')
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, str(script)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+    assert r.returncode == 0 and b'CAPTURE OK' in r.stdout, r.stdout.decode()[-3000:]
