@@ -786,3 +786,34 @@ print('CAPTURE OK')
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     r = subprocess.run([sys.executable, str(script)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
     assert r.returncode == 0 and b'CAPTURE OK' in r.stdout, r.stdout.decode()[-3000:]
+
+
+def test_maximum_vehicle_count(dm):
+    """V = CE2E_MAX_VEH = 256 vehicles per row (D = 1033) against the oracle; one more is refused."""
+    from env_build_b200 import _lib, synthetic as syn
+    rng = np.random.default_rng(256)
+    task, B, V = 'straight', 301, _lib.MAX_VEH
+    modes = tiled(task, V)
+    model = dm.EnvironmentModel(task, mode='training', veh_mode_list=modes)
+    ref = syn.make_ref_indexes(rng, B)
+    obs = syn.make_obs(rng, B, task, V, model.ref_path.path_list, ref)
+    act = syn.make_actions(rng, 1, B)[0]
+    model.reset(obs, ref)
+    res = model.rollout_out(act)
+    om = orc.EnvironmentModel(task, mode='training', path_list=model.ref_path.path_list, veh_mode_list=modes)
+    om.reset(obs, ref)
+    sc = orc.action_transformation(act)
+    want5 = orc.compute_rewards(obs, sc, task)[:5]
+    want, margin = om.compute_next_obses(obs, sc, return_margin=True)
+    got = res[0].numpy()
+    assert got.shape == (B, 9 + 4 * V)
+    for a, b in zip(res[1:], want5):
+        close(a.numpy(), b)
+    close(got[:, :6], want[:, :6])
+    close(got[:, 9:], want[:, 9:])
+    ok = margin > 1e-4
+    close(got[ok, 6:9], want[ok, 6:9])
+    with pytest.raises(ValueError):
+        big = dm.EnvironmentModel(task, mode='training', veh_mode_list=tiled(task, V + 1))
+        big.reset(np.zeros((4, 9 + 4 * (V + 1)), np.float32), np.zeros(4, np.int32))
+        big.rollout_out(np.zeros((4, 2), np.float32))
