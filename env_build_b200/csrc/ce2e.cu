@@ -537,9 +537,10 @@ k_model_step(const __grid_constant__ StepParams P) {
             const int cnt = (int)(qa - q_lane) >> 7;
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
+                // every queued dd is < 12.25, so sqrt(dd) - 3.5 < 0 holds (the gate is that test)
                 const float d = __fsqrt_rn(lds_f32(q_lane + (unsigned)i * 128u));
                 const float g35 = d - 3.5f, g25 = d - 2.5f;
-                v2v_tr = v2v_tr + ((g35 < 0.0f) ? sq(g35) : 0.0f);
+                v2v_tr = v2v_tr + sq(g35);
                 v2v_re = v2v_re + ((g25 < 0.0f) ? sq(g25) : 0.0f);
             }
             qa = q_lane;
