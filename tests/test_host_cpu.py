@@ -183,3 +183,49 @@ def test_candidate_grid_contains_bruteforce_argmin(lib, task):
         # near the path the ranges are a handful of waypoints (that is the point of the grid)
         d2 = ((xs[inside][:20000, None] - wx[None, :]) ** 2 + (ys[inside][:20000, None] - wy[None, :]) ** 2).min(1)
         assert (hi - lo + 1)[:20000][d2 < 9].max() <= 8
+
+
+@pytest.mark.parametrize('kind', ['loop', 'zigzag', 'duplicates', 'random_walk', 'short'])
+def test_candidate_grid_arbitrary_paths(lib, kind):
+    """The C ABI accepts any path table (ce2e_paths_create), so the exactness of the candidate grid must
+    not depend on the three built-in geometries: self-crossing loops, jittery zigzags, repeated
+    waypoints (distance ties -> FIRST minimum), random walks, very short tables."""
+    rng = np.random.default_rng({'loop': 1, 'zigzag': 2, 'duplicates': 3, 'random_walk': 4, 'short': 5}[kind])
+    if kind == 'loop':                                 # a figure of eight, crossing itself
+        t = np.linspace(0, 4 * np.pi, 420)
+        wx, wy = 30 * np.sin(t), 20 * np.sin(2 * t)
+    elif kind == 'zigzag':
+        wx = np.linspace(-40, 40, 380)
+        wy = 3 * np.sign(np.sin(np.arange(380) * 1.3)) + rng.normal(0, 0.05, 380)
+    elif kind == 'duplicates':                         # every waypoint three times: ties everywhere
+        t = np.repeat(np.linspace(0, 1, 130), 3)
+        wx, wy = -25 + 50 * t, 10 * np.sin(6 * t)
+    elif kind == 'random_walk':
+        wx, wy = np.cumsum(rng.normal(0, 0.8, 400)), np.cumsum(rng.normal(0, 0.8, 400))
+    else:
+        wx, wy = np.array([0., 1., 2.]), np.array([0., 0.5, 0.])
+    wx, wy = np.ascontiguousarray(wx, np.float32), np.ascontiguousarray(wy, np.float32)
+    spec = np.zeros(5, np.float32)
+    assert lib.ce2e_grid_build_host(wx.ctypes.data, wy.ctypes.data, len(wx), spec.ctypes.data, None, 0) == 0
+    x0, y0, inv_h, nx, ny = spec[0], spec[1], spec[2], int(spec[3]), int(spec[4])
+    cells = np.zeros(nx * ny, np.uint32)
+    assert lib.ce2e_grid_build_host(wx.ctypes.data, wy.ctypes.data, len(wx), spec.ctypes.data, cells.ctypes.data,
+                                    cells.size) == 0
+    n = 40000
+    k = rng.integers(0, len(wx), n)
+    pts = np.concatenate([
+        np.stack([wx[k] + rng.normal(0, 1.0, n), wy[k] + rng.normal(0, 1.0, n)], 1),
+        np.stack([rng.uniform(x0, x0 + nx / inv_h, n), rng.uniform(y0, y0 + ny / inv_h, n)], 1),
+        np.stack([wx[k], wy[k]], 1),
+        np.stack([(wx[k] + wx[(k + 1) % len(wx)]) / 2, (wy[k] + wy[(k + 1) % len(wx)]) / 2], 1)]).astype(np.float32)
+    xs, ys = pts[:, 0], pts[:, 1]
+    d2 = np.square(xs[:, None] - wx[None, :]) + np.square(ys[:, None] - wy[None, :])      # fp32, DM:712
+    want = d2.argmin(1)                                                                   # first minimum
+    tx = (xs - np.float32(x0)) * np.float32(inv_h)
+    ty = (ys - np.float32(y0)) * np.float32(inv_h)
+    inside = (tx >= 0) & (ty >= 0) & (tx < np.float32(nx)) & (ty < np.float32(ny))
+    c = cells[(ty[inside].astype(np.int32) * nx + tx[inside].astype(np.int32))]
+    lo, hi = (c & 0xffff).astype(np.int64), (c >> 16).astype(np.int64)
+    w = want[inside]
+    assert inside.mean() > 0.5
+    assert ((lo <= w) & (w <= hi)).all(), (kind, int(((lo > w) | (w > hi)).sum()))
