@@ -229,3 +229,11 @@ def test_candidate_grid_arbitrary_paths(lib, kind):
     w = want[inside]
     assert inside.mean() > 0.5
     assert ((lo <= w) & (w <= hi)).all(), (kind, int(((lo > w) | (w > hi)).sum()))
+
+
+def test_makefile_flags_match():
+    """The Makefile builds the same library as env_build_b200._lib.build()."""
+    from env_build_b200 import _lib
+    mk = open(os.path.join(ROOT, 'Makefile')).read()
+    line = [l for l in mk.splitlines() if l.startswith('NVCC_FLAGS')][0]
+    assert line.split(':=')[1].split() == _lib.NVCC_FLAGS
