@@ -38,6 +38,8 @@ SIGNATURES = {
     'ce2e_last_error': (_c.c_char_p, []),
     'ce2e_launch_count': (_i64, []),
     'ce2e_set_fast_trig': (_i, [_i]),
+    'ce2e_set_tma': (_i, [_i]),
+    'ce2e_last_step_kernel': (_i, []),
     'ce2e_paths_create': (_i, [_i, _i, _c.POINTER(_c.c_int32), _c.POINTER(_vp), _c.POINTER(_vp),
                                _c.POINTER(_vp), _c.POINTER(_vp)]),
     'ce2e_paths_destroy': (_i, [_vp]),
@@ -52,6 +54,8 @@ SIGNATURES = {
                                      _vp, _i64, _i64, _vp]),
     'ce2e_env_step': (_i, [_vp, _vp, _vp, _i64, _vp, _c.POINTER(TurnClasses), _i, _i, _i, _vp, _i64, _vp, _vp, _vp,
                            _vp, _i64, _vp]),
+    'ce2e_env_reset': (_i, [_vp, _c.c_uint64, _vp, _vp, _i, _vp, _i64, _vp, _vp, _i, _i, _i64, _vp]),
+    'ce2e_philox4x32': (None, [_c.POINTER(_c.c_uint32), _c.POINTER(_c.c_uint32), _c.POINTER(_c.c_uint32)]),
     'ce2e_judge_done': (_i, [_i, _vp, _i64, _vp, _i, _i, _i, _vp, _i64, _vp]),
     'ce2e_veh_predict': (_i, [_vp, _i64, _c.POINTER(TurnClasses), _i, _vp, _i64, _i64, _vp]),
     'ce2e_rollout_step': (_i, [_vp, _i, _vp, _vp, _i64, _vp, _c.POINTER(TurnClasses), _i, _i, _i,
@@ -124,6 +128,11 @@ def make_turn_classes(classes):
     for i, c in enumerate(classes):
         t.tc[i] = int(c)
     return t
+
+
+def set_tma(enable):
+    """See ce2e_set_tma in include/ce2e.h (on by default).  Returns the previous setting."""
+    return bool(load().ce2e_set_tma(int(bool(enable))))
 
 
 def set_fast_trig(enable):

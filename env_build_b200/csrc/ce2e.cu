@@ -17,6 +17,7 @@
 #include "ce2e.h"
 #include "ce2e_device.cuh"
 #include "ce2e_grid.h"
+#include "ce2e_rng.h"
 
 #include <atomic>
 #include <cstdarg>
@@ -34,8 +35,12 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int64_t g_launches = 0;
+thread_local int g_last_step_kernel = 0;   // 1: k_model_step (cp.async), 2: k_model_step_pair (TMA)
 bool g_use_pdl = getenv("CE2E_NO_PDL") == nullptr;
 bool g_fast_trig = false;
+// A/B switch: ego columns through TMA boxes too (bit 0: loads, bit 1: stores); CE2E_EGO_TMA=0..3
+int g_ego_tma = getenv("CE2E_NO_EGO_TMA") ? 0 : (getenv("CE2E_EGO_TMA") ? atoi(getenv("CE2E_EGO_TMA")) : 3);
+bool g_use_tma = getenv("CE2E_NO_TMA") == nullptr;   // warp-pair TMA kernel for the fused step (ce2e_set_tma)
 
 int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -634,6 +639,8 @@ k_model_step(const __grid_constant__ StepParams P) {
     }
 }
 
+#include "ce2e_step_pair.cuh"
+
 GridView make_grid_view(const ce2e_paths *p) {
     GridView g;
     memset(&g, 0, sizeof(g));
@@ -649,13 +656,84 @@ GridView make_grid_view(const ce2e_paths *p) {
     return g;
 }
 
+constexpr int CE2E_ERR_NOTMA = -1000;      // internal: fall back to k_model_step
+
+// The warp-pair TMA kernel serves the fused rollout_out step on rows whose vehicle block is 16 B
+// aligned in both buffers (what padded_rows / any ld % 4 == 0 layout with an aligned block gives).
+bool pair_kernel_applies(const StepParams &P, const DeviceInfo *di) {
+    const int need = F_REWARD | F_NEXT | F_VEC_IN | F_VEC_OUT;
+    return g_use_tma && P.horizon == 0 && (P.flags & need) == need && P.V_in == P.V_out && P.V_in >= 1 &&
+           P.B >= PAIR_ROWS && P.B < ((int64_t)1 << 31) - PAIR_ROWS &&
+           (int)pair_smem_bytes(P.pv.n_paths, P.pv.stride) <= di->max_smem_optin;
+}
+
+int launch_model_step_pair(const StepParams &P, const DeviceInfo *di, cudaStream_t st) {
+    PairParams PP;
+    memset(&PP, 0, sizeof(PP));
+    PP.S = P;
+    const int veh_off = 6 + 3 * (P.n_future + 1), H0 = (P.V_in + 1) >> 1;
+    for (int h = 0; h < 2; ++h) {
+        const int n_veh = h ? P.V_in - H0 : H0;
+        if (n_veh == 0) continue;
+        const int off = veh_off + (h ? 4 * H0 : 0);
+        if (!vehicle_tensor_map(P.obs_in + off, P.ld_in, P.B, n_veh, &PP.tm_in[h]) ||
+            !vehicle_tensor_map(P.obs_out + off, P.ld_out, P.B, n_veh, &PP.tm_out[h]))
+            return CE2E_ERR_NOTMA;
+    }
+    // ego + tracking columns as one more box per tile when they are the 9 floats right in front of the
+    // vehicle block (n = 0); the store also rewrites the 28 B in front of each row, which must then be
+    // padding of the previous row (ld - D >= 7, what padded_rows gives).  The maps start at row 1.
+    if (veh_off == 9 && g_ego_tma) {
+        if (g_ego_tma & 1)
+            PP.ego_tma_in = vehicle_tensor_map(P.obs_in + P.ld_in - 7, P.ld_in, P.B - 1, 4, &PP.tm_ego_in, true);
+        if ((g_ego_tma & 2) && P.ld_out - (9 + 4 * P.V_out) >= 7)
+            PP.ego_tma_out = vehicle_tensor_map(P.obs_out + P.ld_out - 7, P.ld_out, P.B - 1, 4, &PP.tm_ego_out, true);
+    }
+    const bool fast = g_fast_trig;
+    void (*kern)(const PairParams) = fast ? k_model_step_pair<true> : k_model_step_pair<false>;
+    static std::atomic<bool> smem_set[64][2];
+    int dev = 0;
+    CE2E_CUDA(cudaGetDevice(&dev));
+    std::atomic<bool> &set = smem_set[dev & 63][fast ? 1 : 0];
+    if (!set.load(std::memory_order_acquire)) {
+        CE2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di->max_smem_optin));
+        set.store(true, std::memory_order_release);
+    }
+    const int64_t n_tiles = (P.B + PAIR_ROWS - 1) / PAIR_ROWS;
+    const int64_t max_blocks = 2 * (int64_t)di->sms;
+    const int64_t blocks = n_tiles < max_blocks ? n_tiles : max_blocks;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(PAIR_WARPS * 32);
+    cfg.dynamicSmemBytes = pair_smem_bytes(P.pv.n_paths, P.pv.stride);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, PP);
+    ++g_launches;
+    g_last_step_kernel = 2;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CE2E_ERR_CUDA, "k_model_step_pair launch: %s", cudaGetErrorString(e));
+    }
+    return CE2E_OK;
+}
+
 int launch_model_step(StepParams &P, cudaStream_t st) {
     DeviceInfo *di;
     int rc = device_info(&di);
     if (rc) return rc;
     if (P.ld_in > (1 << 24) || P.ld_out > (1 << 24)) return fail(CE2E_ERR_SHAPE, "row stride too large");
-    const int64_t n_tiles = (P.B + RPW - 1) / RPW;
     const bool fused = P.horizon > 0;
+    if (pair_kernel_applies(P, di)) {
+        rc = launch_model_step_pair(P, di, st);
+        if (rc != CE2E_ERR_NOTMA) return rc;       // no tensor-map encoder in this driver: k_model_step below
+    }
+    const int64_t n_tiles = (P.B + RPW - 1) / RPW;
     size_t smem = (size_t)P.pv.n_paths * P.pv.stride * 12 + 32 +
                   STEP_WARPS * (fused ? sizeof(WarpScratchT<FUSED_MAX_CHUNKS>) : sizeof(WarpScratch));
     if ((int)smem > di->max_smem_optin)
@@ -698,6 +776,7 @@ int launch_model_step(StepParams &P, cudaStream_t st) {
     cfg.numAttrs = g_use_pdl ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, P);
     ++g_launches;
+    g_last_step_kernel = 1;
     if (e != cudaSuccess) {
         cudaGetLastError();
         return fail(CE2E_ERR_CUDA, "k_model_step launch: %s", cudaGetErrorString(e));
@@ -1401,6 +1480,77 @@ __global__ void k_select_vehicles(const __grid_constant__ SelectSpec spec, int t
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// on-device reset of the batched environment (E2E:99-127, E2E:472-499)
+// ------------------------------------------------------------------------------------------
+// CrossroadEnd2end.reset -> _reset_init_state for every row whose done code is non-zero (or for all
+// rows when `done` is NULL): a random waypoint index int(u * span) + 700 on the row's path (span =
+// 1400 / 1700 / 920, E2E:473-478), ego = (v_x = 8 u', 0, 0, x, y, phi of that waypoint) (E2E:480-499),
+// tracking columns = tracking_error_vector of that pose (E2E:293-297).  The reference then asks SUMO
+// for the surrounding traffic (traffic.py:151-195, out of scope); here the V vehicle slots are drawn
+// from the synthetic traffic distribution of SURVEY 8d (10 % within +-8 m of the ego, the rest uniform
+// over the +-65 m map, pushed 30 m away if closer than 6 m; v ~ U(0, 8); heading on a compass
+// direction + ~N(0, 10 deg) as the scaled sum of four uniforms).  All draws are Philox4x32-10 outputs
+// keyed by `seed` at counter (row, episode[row], draw block); episode[row] is incremented.  One thread
+// per row; rows that are not done return at once.
+struct ResetParams {
+    PathView pv;
+    GridView gv;
+    const float *full[CE2E_MAX_PATHS];
+    int task, fixed_path, V, n_future, span;
+    uint32_t seed_lo, seed_hi;
+};
+
+__global__ void k_env_reset(const __grid_constant__ ResetParams R, int32_t *__restrict__ episode,
+                            const int8_t *__restrict__ done, float *__restrict__ obs, int64_t ld,
+                            int32_t *__restrict__ ref_idx, int8_t *__restrict__ virtual_red, int64_t B) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    if (done && done[i] == 0) return;
+    const uint32_t ep = (uint32_t)episode[i];
+    episode[i] = (int32_t)(ep + 1u);
+    const uint32_t i_lo = (uint32_t)i, i_hi = (uint32_t)((uint64_t)i >> 32);
+    const Philox4 r = philox4x32_10(i_lo, i_hi, ep, 0u, R.seed_lo, R.seed_hi);
+    const int p = R.fixed_path >= 0 ? R.fixed_path : (int)(((uint64_t)r.v[0] * (uint32_t)R.pv.n_paths) >> 32);
+    const int L = R.pv.L[p];
+    int idx = (int)(((uint64_t)r.v[1] * (uint32_t)R.span) >> 32) + 700;         // E2E:473-478
+    idx = idx < L ? idx : L - 1;                                                 // indexs2points clamp, DM:727-728
+    const float *tab = R.full[p];
+    const float x = tab[idx], y = tab[L + idx], phi = tab[2 * (size_t)L + idx];
+    const float v = CE2E_EXP_V * u01_24(r.v[2]);                                 // E2E:482
+    float *o = obs + i * ld;
+    o[0] = v; o[1] = 0.0f; o[2] = 0.0f; o[3] = x; o[4] = y; o[5] = phi;
+    {
+        int k0, k1, bi;
+        float best;
+        const float2 *t_xy = R.pv.xy + (size_t)p * R.pv.stride;
+        candidate_range(R.gv, p, (R.pv.N[p] + 1) & ~1, x, y, k0, k1);
+        scan_min(t_xy, k0, k1, x, y, best, bi);
+        tracking_from_index(t_xy, R.pv.phi + (size_t)p * R.pv.stride, L, R.pv.tail[p], R.task, bi, x, y, phi, v,
+                            R.n_future, o + 6);
+    }
+    float *veh = o + 6 + 3 * (R.n_future + 1);
+    for (int j = 0; j < R.V; ++j) {
+        const Philox4 a = philox4x32_10(i_lo, i_hi, ep, 1u + 2u * (uint32_t)j, R.seed_lo, R.seed_hi);
+        const Philox4 b = philox4x32_10(i_lo, i_hi, ep, 2u + 2u * (uint32_t)j, R.seed_lo, R.seed_hi);
+        const bool near = (a.v[0] & 0xffffu) < 6554u;
+        const int quad = (int)((a.v[0] >> 16) & 3u);
+        const float u1 = u01_24(a.v[1]), u2 = u01_24(a.v[2]), u3 = u01_24(a.v[3]);
+        float vx = near ? x + (u1 * 16.0f - 8.0f) : u1 * 130.0f - 65.0f;
+        const float vy = near ? y + (u2 * 16.0f - 8.0f) : u2 * 130.0f - 65.0f;
+        const float dd = sq(vx - x) + sq(vy - y);
+        vx = (dd < 36.0f) ? vx + 30.0f : vx;
+        const float s4 = ((u01_24(b.v[0]) + u01_24(b.v[1])) + u01_24(b.v[2])) + u01_24(b.v[3]);
+        const float base = quad == 0 ? 0.0f : (quad == 1 ? 90.0f : (quad == 2 ? 180.0f : -90.0f));
+        float vphi = base + 10.0f * ((s4 - 2.0f) * 1.73205077648162842f);
+        vphi = (vphi > 180.0f) ? vphi - 360.0f : vphi;
+        vphi = (vphi <= -180.0f) ? vphi + 360.0f : vphi;
+        veh[4 * j] = vx; veh[4 * j + 1] = vy; veh[4 * j + 2] = CE2E_EXP_V * u3; veh[4 * j + 3] = vphi;
+    }
+    ref_idx[i] = p;
+    if (virtual_red) virtual_red[i] = (int8_t)(u01_24(r.v[3]) > 0.9f);             // E2E:120-124
+}
+
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 int check_task(int task) {
@@ -1499,6 +1649,12 @@ int ce2e_set_fast_trig(int enable) {
     g_fast_trig = enable != 0;
     return old;
 }
+int ce2e_set_tma(int enable) {
+    const int old = g_use_tma;
+    g_use_tma = enable != 0;
+    return old;
+}
+int ce2e_last_step_kernel(void) { return g_last_step_kernel; }
 const char *ce2e_last_error(void) { return g_err; }
 int64_t ce2e_launch_count(void) { return g_launches; }
 
@@ -1711,6 +1867,33 @@ int ce2e_env_step(const ce2e_paths *paths, const int32_t *ref_idx, const float *
     if (rc || B == 0) return rc;
     return launch_env_done(paths->task, obs_out, ld_out, act_scaled_out, V, 6 + 3 * (n_future + 1), v_light, done_out,
                            B, (cudaStream_t)stream);
+}
+
+int ce2e_env_reset(const ce2e_paths *paths, uint64_t seed, int32_t *episode, const int8_t *done, int fixed_path,
+                   float *obs, int64_t ld, int32_t *ref_idx, int8_t *virtual_red, int V, int n_future, int64_t B,
+                   void *stream) {
+    int rc;
+    if ((rc = check_batch(B))) return rc;
+    if (B == 0) return CE2E_OK;
+    if (!paths || !episode || !obs || !ref_idx) return fail(CE2E_ERR_NULL, "NULL argument");
+    if (V < 0 || V > CE2E_MAX_VEH || n_future < 0 || ld < 6 + 3 * (n_future + 1) + 4 * V)
+        return fail(CE2E_ERR_SHAPE, "bad V / n_future / ld");
+    if (fixed_path >= paths->n_paths) return fail(CE2E_ERR_PATH, "fixed_path %d outside [0, %d)", fixed_path, paths->n_paths);
+    ResetParams R;
+    memset(&R, 0, sizeof(R));
+    R.pv = make_view(paths);
+    R.gv = make_grid_view(paths);
+    for (int i = 0; i < paths->n_paths; ++i) R.full[i] = paths->full[i];
+    R.task = paths->task; R.fixed_path = fixed_path < 0 ? -1 : fixed_path; R.V = V; R.n_future = n_future;
+    R.span = paths->task == 0 ? 900 + 500 : (paths->task == 1 ? 1200 + 500 : 420 + 500);    // E2E:473-478
+    R.seed_lo = (uint32_t)seed; R.seed_hi = (uint32_t)(seed >> 32);
+    k_env_reset<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(R, episode, done, obs, ld, ref_idx, virtual_red, B);
+    return after_launch("k_env_reset");
+}
+
+void ce2e_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    const Philox4 r = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    for (int i = 0; i < 4; ++i) out[i] = r.v[i];
 }
 
 int ce2e_judge_done(int task, const float *obs, int64_t ld, const float *act_scaled, int V, int n_future,

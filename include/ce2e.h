@@ -66,6 +66,19 @@ const char *ce2e_last_error(void);
  * unchanged.  Returns the previous setting.                                                   */
 int ce2e_set_fast_trig(int enable);
 
+/* Process-wide option, default 1 (environment CE2E_NO_TMA=1 starts with 0).  enable != 0: the fused
+ * step (ce2e_rollout_step / ce2e_env_step; EnvironmentModel.rollout_out, DM:118-126) runs the
+ * warp-pair kernel that streams the vehicle block with TMA tensor-map copies whenever the vehicle block
+ * of obs_in and obs_out is 16-byte aligned with ld % 4 == 0, V_in == V_out >= 1 and B >= 32; otherwise,
+ * and with enable == 0, the cp.async kernel runs.  Both give bit-identical results.  Returns the
+ * previous setting.                                                                            */
+int ce2e_set_tma(int enable);
+
+/* Which kernel the calling thread's last fused-step launch (rollout_out, DM:118-126) used: 0 none
+ * yet, 1 k_model_step (cp.async staging), 2 k_model_step_pair (TMA tensor-map staging).
+ * Diagnostic only.                                                                             */
+int ce2e_last_step_kernel(void);
+
 /* Number of CUDA kernels this library has launched from the calling thread since load. */
 int64_t ce2e_launch_count(void);
 
@@ -152,6 +165,23 @@ int ce2e_env_step(const ce2e_paths *paths, const int32_t *ref_idx, const float *
                   const float *act_norm, const ce2e_turn_classes *turn, int V, int n_future, int v_light,
                   float *obs_out, int64_t ld_out, float *out5, float *dict16, float *act_scaled_out,
                   int8_t *done_out, int64_t B, void *stream);
+
+/* CrossroadEnd2end.reset / _reset_init_state (E2E:99-127, E2E:472-499) for the batched environment, on
+ * the device: every row i with done[i] != 0 (done == NULL: every row) starts a new episode -- waypoint
+ * index int(u * span) + 700 on its path (E2E:473-478), ego = (8 u', 0, 0, x, y, phi) (E2E:480-499),
+ * tracking columns re-projected (E2E:293-297), the V vehicle slots refilled from the synthetic traffic
+ * distribution (the reference asks SUMO, traffic.py:151-195 -- out of scope), ref_idx[i] = fixed_path, or
+ * a uniformly drawn path if fixed_path < 0.  Draws are Philox4x32-10 at counter (i, episode[i], block)
+ * under key `seed`; episode[i] ([B] int32, caller-initialised) is incremented for the rows reset.
+ * virtual_red ([B] int8 or NULL) receives the 10 % virtual-red-light flag of E2E:120-124.
+ * No host synchronisation: capturable together with ce2e_env_step.                               */
+int ce2e_env_reset(const ce2e_paths *paths, uint64_t seed, int32_t *episode, const int8_t *done,
+                   int fixed_path, float *obs, int64_t ld, int32_t *ref_idx, int8_t *virtual_red, int V,
+                   int n_future, int64_t B, void *stream);
+
+/* HOST function: one Philox4x32-10 block, the generator behind ce2e_env_reset's draws (E2E:473, E2E:482
+ * use np.random.random()), exported so that tests can pin it against known-answer vectors.        */
+void ce2e_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
 /* CrossroadEnd2end._judge_done (E2E:200-256) with Traffic.collision_check (traffic.py:263-295) on
  * observations obs [B,D] taken AFTER a step; act_scaled [B,2] = the scaled action of that step

@@ -817,3 +817,63 @@ def test_maximum_vehicle_count(dm):
         big = dm.EnvironmentModel(task, mode='training', veh_mode_list=tiled(task, V + 1))
         big.reset(np.zeros((4, 9 + 4 * (V + 1)), np.float32), np.zeros(4, np.int32))
         big.rollout_out(np.zeros((4, 2), np.float32))
+
+
+# ------------------------------------------------------------------------------------------
+# the warp-pair TMA kernel against the cp.async kernel (same arithmetic, same summation order)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('task,V,n,mode', [('left', 32, 0, 'training'), ('left', 8, 0, 'selecting'),
+                                           ('straight', 9, 0, 'training'), ('right', 5, 0, 'training'),
+                                           ('left', 1, 0, 'training'), ('left', 2, 3, 'training'),
+                                           ('straight', 33, 10, 'selecting'), ('right', 40, 0, 'training'),
+                                           ('left', 256, 0, 'training')])
+def test_tma_kernel_equals_cp_async_kernel(dm, task, V, n, mode):
+    """ce2e_set_tma(1) (k_model_step_pair: 2-D tensor-map loads / stores, warp pair per 32 rows) and
+    ce2e_set_tma(0) (k_model_step: cp.async, two lanes per row) must agree bit for bit on every output,
+    for ragged batch sizes around the 32-row tile and for odd / tiny / maximal vehicle counts."""
+    from env_build_b200 import _lib, synthetic as syn
+    rng = np.random.default_rng(1000 + V + n)
+    for B in (32, 33, 95, 4097):
+        model = dm.EnvironmentModel(task, n, mode=mode, veh_mode_list=tiled(task, V))
+        ref = syn.make_ref_indexes(rng, B, out_of_range_frac=0.05)
+        obs = syn.make_obs(rng, B, task, V, model.ref_path.path_list, ref if mode == 'training' else 1, n)
+        act = syn.make_actions(rng, 2, B)
+        res = {}
+        for tma in (True, False):
+            old = _lib.set_tma(tma)
+            try:
+                n0 = _lib.launch_count()
+                if mode == 'training':
+                    model.reset(obs, ref)
+                else:
+                    model.add_traj(obs, 1)
+                outs = []
+                for t in range(2):                          # two steps: the second reads what the first stored
+                    outs.append([r.numpy().copy() for r in model.rollout_out(act[t])])
+                res[tma] = outs
+                assert _lib.launch_count() - n0 == 2
+            finally:
+                _lib.set_tma(old)
+        for a, b in zip(res[True], res[False]):
+            for x, y in zip(a, b):
+                bits_equal(x, y)
+
+
+def test_tma_kernel_is_the_default_path(dm):
+    """The fused step on padded rows must launch k_model_step_pair (checked through the kernel's name in
+    a profiler-free way: the two kernels need different dynamic shared memory, which the library reports
+    through ce2e_last_step_kernel)."""
+    from env_build_b200 import _lib, synthetic as syn
+    rng = np.random.default_rng(5)
+    model = dm.EnvironmentModel('left', mode='training', veh_mode_list=tiled('left', 32))
+    ref = syn.make_ref_indexes(rng, 256)
+    obs = syn.make_obs(rng, 256, 'left', 32, model.ref_path.path_list, ref)
+    model.reset(obs, ref)
+    model.rollout_out(syn.make_actions(rng, 1, 256)[0])
+    assert _lib.load().ce2e_last_step_kernel() == 2           # 2 = k_model_step_pair (TMA)
+    old = _lib.set_tma(False)
+    try:
+        model.rollout_out(syn.make_actions(rng, 1, 256)[0])
+        assert _lib.load().ce2e_last_step_kernel() == 1       # 1 = k_model_step (cp.async)
+    finally:
+        _lib.set_tma(old)
