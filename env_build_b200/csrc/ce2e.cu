@@ -700,7 +700,7 @@ int launch_model_step_pair(const StepParams &P, const DeviceInfo *di, cudaStream
         set.store(true, std::memory_order_release);
     }
     const int64_t n_tiles = (P.B + PAIR_ROWS - 1) / PAIR_ROWS;
-    const int64_t max_blocks = 2 * (int64_t)di->sms;
+    const int64_t max_blocks = PAIR_BLOCKS_PER_SM * (int64_t)di->sms;
     const int64_t blocks = n_tiles < max_blocks ? n_tiles : max_blocks;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -68,6 +68,8 @@ class CrossroadEnd2end(object):
                  veh_num=None,
                  auto_reset=False,
                  traffic_init=None,
+                 reward_info=True,
+                 use_graph=False,
                  **kwargs):
         self.dynamics = VehicleDynamics()
         self.training_task = training_task
@@ -90,7 +92,13 @@ class CrossroadEnd2end(object):
         self.observation_space = Box(low=-np.inf, high=np.inf, shape=(self.obs_dim,), dtype=np.float32)
         self.mode = mode
         self.auto_reset = auto_reset
+        # traffic_init(rng, ego_xy, task, V) -> [n, V, 4]: host-side initial traffic (resets then go through
+        # the host); None: resets run on the device (ce2e_env_reset), no host round trip
         self.traffic_init = traffic_init
+        self.reward_info_enabled = bool(reward_info)     # the 16-term reward dict triples the step's writes
+        self.use_graph = bool(use_graph)                 # replay step() as a CUDA graph (batched, device reset)
+        self._bufs = None                                # static state, allocated by reset()
+        self._graphs = [None, None]
         self.v_light = 0                     # the model traffic has no signal phases: always green
         self.done_type = 'not_done_yet'
         self.reward_info = None
@@ -103,15 +111,25 @@ class CrossroadEnd2end(object):
     # -- gym plumbing ---------------------------------------------------------------------------
     def seed(self, seed=None):
         self.np_random = np.random.default_rng(seed)
+        # key of the device-side draws (ce2e_env_reset: Philox4x32-10 at counter (env, episode, block))
+        self._seed = int(seed) & (2 ** 64 - 1) if seed is not None else int(self.np_random.integers(0, 2 ** 63))
         return [seed]
 
     def close(self):
+        self._graphs = [None, None]
         self.ref_path.close()
 
     def set_traj(self, trajectory):
-        """set the real trajectory to reconstruct observation (E2E:793-795)"""
+        """set the real trajectory to reconstruct observation (E2E:793-795): every environment now
+        follows `trajectory` (its ref_index), and the tracking columns of the current observation are
+        re-projected onto it, which is what the reference's `env.set_traj(path); env._get_obs()` yields
+        (hier_decision.py:115-124, multi_ego.py:104)."""
         self.ref_path = trajectory
         self.env_model.ref_path = trajectory
+        self._graphs = [None, None]                      # captured steps hold the old table handle
+        if self.obs is not None:
+            self.ref_indexes.fill_(int(trajectory.ref_index))
+            self._fill_tracking(self.obs, self.ref_indexes)
 
     def _squeeze(self, t):
         return t.numpy()[0] if self.num_envs == 1 else t
@@ -147,59 +165,138 @@ class CrossroadEnd2end(object):
                                                   self.num_future_data, ref_indexes=ref_dev)
         obs_dev[:, 6:6 + trk.shape[1]] = trk
 
+    def _alloc(self):
+        B, dev = self.num_envs, torch.device('cuda', torch.cuda.current_device())
+        veh_off = 6 + 3 * (self.num_future_data + 1)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self._bufs = dict(obs=[padded_rows(B, self.obs_dim, veh_off, dev) for _ in range(2)],
+                          out5=torch.zeros((5, B), **f32),
+                          d16=torch.zeros((16, B), **f32) if self.reward_info_enabled else None,
+                          scaled=torch.zeros((B, 2), **f32), act=torch.zeros((B, 2), **f32),
+                          done=torch.zeros((B,), dtype=torch.int8, device=dev),
+                          episode=torch.zeros((B,), dtype=torch.int32, device=dev),
+                          ref=torch.zeros((B,), dtype=torch.int32, device=dev),
+                          red=torch.zeros((B,), dtype=torch.int8, device=dev))
+        for b in self._bufs['obs']:
+            b.zero_()
+        self._cur = 0
+
+    def _device_reset(self, obs, done):
+        """ce2e_env_reset on the rows of `obs` whose `done` code is non-zero (done None: all rows)."""
+        fixed = -1 if self.num_envs > 1 and self._fixed_path is None else int(
+            self.ref_path.ref_index if self._fixed_path is None else self._fixed_path)
+        b = self._bufs
+        _lib.check(_lib.load().ce2e_env_reset(self.ref_path.handle, ctypes.c_uint64(self._seed), _ptr(b['episode']),
+                                              _ptr(done), fixed, _ptr(obs), obs.stride(0), _ptr(b['ref']), _ptr(b['red']),
+                                              self.veh_num, int(self.num_future_data), self.num_envs, _stream()))
+
     def reset(self, **kwargs):
+        """E2E:99-127.  Batched environments draw their path per row; `reset(ref_index=k)` (the
+        reference's ReferencePath kwargs) pins every row to path k."""
+        self._graphs = [None, None]
         if kwargs:
             self.ref_path = ReferencePath(self.training_task, **kwargs)      # E2E:100
             self.env_model.ref_path = self.ref_path
         elif self.num_envs == 1:                                             # E2E:100 -> DM:591: a fresh random path
             self.ref_path.set_path(int(self.np_random.integers(len(self.ref_path.path_list))))
-        obs, ref = self._reset_rows(self.num_envs)
-        veh_off = 6 + 3 * (self.num_future_data + 1)
-        buf = padded_rows(self.num_envs, self.obs_dim, veh_off)
-        buf.copy_(to_device(obs))
-        self.ref_indexes = to_device(ref, torch.int32)
-        self._fill_tracking(buf, self.ref_indexes)
+        self._fixed_path = int(self.ref_path.ref_index) if (kwargs.get('ref_index') is not None or self.num_envs == 1) \
+            else None
+        if self._bufs is None:
+            self._alloc()
+        b = self._bufs
+        buf = b['obs'][self._cur]
+        self.ref_indexes = b['ref']
+        if self.traffic_init is None:
+            self._device_reset(buf, None)
+        else:
+            obs, ref = self._reset_rows(self.num_envs)
+            buf.copy_(to_device(obs))
+            self.ref_indexes.copy_(to_device(ref, torch.int32))
+            self._fill_tracking(buf, self.ref_indexes)
         self.obs = _wrap(buf)
         self.action = None
         self.reward_info = None
         self.done_type = 'not_done_yet'
+        self.virtual_red_light_vehicle = bool(b['red'][0].item()) if (self.num_envs == 1 and self.mode == 'training') \
+            else False                                                       # E2E:119-126
         return self._squeeze(self.obs)
 
     # -- step -------------------------------------------------------------------------------------
-    def step(self, action):
-        B = self.num_envs
-        act = to_device(np.asarray(action, np.float32) if not isinstance(action, torch.Tensor) else action)
-        act = act.reshape(B, 2).contiguous()
-        obs = self.obs
-        veh_off = 6 + 3 * (self.num_future_data + 1)
-        nxt = padded_rows(B, self.obs_dim, veh_off, obs.device)
-        out5 = torch.empty((5, B), dtype=torch.float32, device=obs.device)
-        d16 = torch.empty((16, B), dtype=torch.float32, device=obs.device)
-        scaled = torch.empty((B, 2), dtype=torch.float32, device=obs.device)
-        done = torch.empty((B,), dtype=torch.int8, device=obs.device)
-        _lib.check(_lib.load().ce2e_env_step(self.ref_path.handle, _ptr(self.ref_indexes), _ptr(obs), obs.stride(0),
-                                             _ptr(act), ctypes.byref(self._turn), self.veh_num,
+    def _enqueue_step(self, cur):
+        """One environment step on the static buffers: the fused model step + done kernel
+        (ce2e_env_step) and, with auto_reset on the device path, the reset kernel.  No allocation, no
+        host synchronisation: capturable."""
+        b = self._bufs
+        obs, nxt = b['obs'][cur], b['obs'][1 - cur]
+        _lib.check(_lib.load().ce2e_env_step(self.ref_path.handle, _ptr(b['ref']), _ptr(obs), obs.stride(0),
+                                             _ptr(b['act']), ctypes.byref(self._turn), self.veh_num,
                                              int(self.num_future_data), int(self.v_light), _ptr(nxt), nxt.stride(0),
-                                             _ptr(out5), _ptr(d16), _ptr(scaled), _ptr(done), B, _stream()))
-        self.action = _wrap(scaled)
-        self.obs = _wrap(nxt)
-        self.done_code = _wrap(done)
-        reward = out5[0]
+                                             _ptr(b['out5']), _ptr(b['d16']), _ptr(b['scaled']), _ptr(b['done']),
+                                             self.num_envs, _stream()))
+        if self.auto_reset and self.num_envs > 1 and self.traffic_init is None:
+            self._device_reset(nxt, b['done'])
+
+    def step(self, action):
+        """E2E:132-144.  Batched environments return views of static device buffers (observations,
+        rewards, done flags, info tensors): they are overwritten by the next step() -- clone what must
+        be kept.  With auto_reset the returned observation rows of finished environments are already
+        those of their next episode, and `done` still flags them."""
+        B = self.num_envs
+        if self._bufs is None:
+            raise RuntimeError('call reset() before step()')
+        b = self._bufs
+        act = to_device(np.asarray(action, np.float32) if not isinstance(action, torch.Tensor) else action)
+        b['act'].copy_(act.reshape(B, 2), non_blocking=True)
+        cur = self._cur
+        # a caller may have assigned env.obs / env.ref_indexes (the reference's attributes): adopt them
+        if self.obs is not None and self.obs.data_ptr() != b['obs'][cur].data_ptr():
+            b['obs'][cur].copy_(to_device(self.obs).reshape(B, self.obs_dim), non_blocking=True)
+        if self.ref_indexes is not None and self.ref_indexes.data_ptr() != b['ref'].data_ptr():
+            b['ref'].copy_(to_device(self.ref_indexes, torch.int32).reshape(B), non_blocking=True)
+            self.ref_indexes = b['ref']
+        if self.use_graph and B > 1 and self.traffic_init is None:
+            if self._graphs[cur] is None:
+                self.ref_path.handle
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    snap = [t.clone() for t in (b['obs'][0], b['obs'][1], b['episode'], b['ref'])]
+                    self._enqueue_step(cur)            # warm-up outside the capture, then undo its effects
+                    for t, c in zip((b['obs'][0], b['obs'][1], b['episode'], b['ref']), snap):
+                        t.copy_(c)
+                torch.cuda.current_stream().wait_stream(s)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue_step(cur)
+                self._graphs[cur] = g
+                for t, c in zip((b['obs'][0], b['obs'][1], b['episode'], b['ref']), snap):
+                    t.copy_(c)                         # (capture does not execute, but keep the state exact)
+            self._graphs[cur].replay()
+        else:
+            self._enqueue_step(cur)
+        self._cur = 1 - cur
+        self.action = _wrap(b['scaled'])
+        self.obs = _wrap(b['obs'][self._cur])
+        self.done_code = _wrap(b['done'])
+        reward, done, d16 = b['out5'][0], b['done'], b['d16']
         if B == 1:
             code = int(done.item())
             self.done_type = DONE_TYPES[code]
-            self.reward_info = {k: float(d16[i, 0]) for i, k in enumerate(REWARD_DICT_KEYS)}
-            self.reward_info.update({'final_rew': float(reward[0])})
+            if d16 is not None:
+                self.reward_info = {k: float(d16[i, 0]) for i, k in enumerate(REWARD_DICT_KEYS)}
+                self.reward_info.update({'final_rew': float(reward[0])})
             info = dict(reward_info=self.reward_info, ref_index=int(self.ref_indexes[0]), done_type=self.done_type,
                         ego_dynamics=self._ego_dynamics_dict())
             return self.obs.numpy()[0], float(reward[0]), int(code != 0), info
-        info = dict(done_code=self.done_code, ref_index=self.ref_indexes,
-                    reward_info={k: _wrap(d16[i]) for i, k in enumerate(REWARD_DICT_KEYS)})
-        if self.auto_reset:
+        info = dict(done_code=self.done_code, ref_index=self.ref_indexes)
+        if d16 is not None:
+            info['reward_info'] = {k: _wrap(d16[i]) for i, k in enumerate(REWARD_DICT_KEYS)}
+        if self.auto_reset and self.traffic_init is not None:
             self._reset_done_rows(done)
         return self.obs, _wrap(reward), _wrap(done != 0), info
 
     def _reset_done_rows(self, done):
+        """Host-side auto-reset, only for a user-supplied `traffic_init` (synchronises)."""
         rows = torch.nonzero(done != 0).reshape(-1)
         n = int(rows.numel())
         if n == 0:
@@ -284,6 +381,9 @@ class CrossroadEnd2end(object):
         return (nxt[0], par[0]) if self.num_envs == 1 else (nxt, par)
 
     def _get_obs(self, exit_='D'):
+        """E2E:285-303: the observation of the current state; its tracking columns are projected onto the
+        CURRENT reference path (self.ref_path / the per-row path indexes), like the reference's."""
+        self._fill_tracking(self.obs, self.ref_indexes)
         return self._squeeze(self.obs)
 
     def render(self, mode='human'):

@@ -793,3 +793,93 @@ def select_interested_vehicles(veh, classes, ego_x, ego_y, task, v_light=0, virt
         for v in chosen:
             out.extend(v)
     return np.array(out, dtype=f32)
+
+
+# ------------------------------------------------------------------------------------------
+# reset of the batched environment (test infrastructure for ce2e_env_reset)
+# ------------------------------------------------------------------------------------------
+RESET_SPAN = dict(left=900 + 500, straight=1200 + 500, right=420 + 500)        # endtoend.py:473-478
+
+
+def reset_init_state(task, path, u_index, u_v):
+    """CrossroadEnd2end._reset_init_state (endtoend.py:472-499) with the two `np.random.random()` draws
+    passed in: (v_x, v_y, r, x, y, phi) of the fresh ego as float32 (the observation dtype)."""
+    random_index = int(u_index * RESET_SPAN[task]) + 700                        # endtoend.py:473-478
+    idx = min(max(random_index, 0), len(path[0]) - 1)                           # indexs2points clamp, DM:727-728
+    x, y, phi = path[0][idx], path[1][idx], path[2][idx]                        # endtoend.py:480
+    v = EXPECTED_V * u_v                                                        # endtoend.py:482
+    return np.array([v, 0., 0., x, y, phi], dtype=np.float32)                   # endtoend.py:489-495
+
+
+def philox4x32_10(ctr, key):
+    """Philox4x32-10 (Salmon et al., SC'11) on arrays: ctr [..., 4], key [..., 2] uint32 -> [..., 4] uint32.
+    The counter-based generator behind ce2e_env_reset (csrc/ce2e_rng.h)."""
+    c = [np.asarray(ctr[..., i], dtype=np.uint64) for i in range(4)]
+    k = [np.asarray(key[..., i], dtype=np.uint64) for i in range(2)]
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), \
+        np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k[0], p1 & MASK, (p0 >> np.uint64(32)) ^ c[3] ^ k[1], p0 & MASK]
+        k = [(k[0] + W0) & MASK, (k[1] + W1) & MASK]
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def _u01_24(r):
+    return (r >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+
+
+def env_reset_rows(seed, rows, episodes, task, path_list, V, num_future_data=0, fixed_path=-1):
+    """NumPy restatement of k_env_reset (csrc/ce2e.cu): fresh observation rows, path indexes and
+    virtual-red-light flags of environments `rows` in their `episodes`-th episode under `seed`.
+    Ego state = reset_init_state with u_index = r1 / 2^32, u_v = (r2 >> 8) / 2^24; traffic slots from the
+    synthetic distribution of SURVEY 8d; every fp32 operation in the kernel's order."""
+    f = np.float32
+    rows = np.asarray(rows, dtype=np.uint64)
+    ep = np.asarray(episodes, dtype=np.uint64)
+    n = len(rows)
+    key = np.empty((n, 2), np.uint32)
+    key[:, 0], key[:, 1] = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
+
+    def block(b):
+        ctr = np.stack([rows & np.uint64(0xFFFFFFFF), rows >> np.uint64(32), ep, np.full(n, b, np.uint64)], -1)
+        return philox4x32_10(ctr.astype(np.uint32), key)
+
+    r = block(0)
+    n_paths = len(path_list)
+    p = np.full(n, fixed_path, np.int64) if fixed_path >= 0 else \
+        ((r[:, 0].astype(np.uint64) * np.uint64(n_paths)) >> np.uint64(32)).astype(np.int64)
+    D = 6 + 3 * (num_future_data + 1) + 4 * V
+    obs = np.zeros((n, D), f)
+    for i in range(n):
+        path = path_list[p[i]]
+        obs[i, :6] = reset_init_state(task, path, float(r[i, 1]) / 2.0 ** 32, float(_u01_24(r[i:i + 1, 2])[0]))
+    trk = np.zeros((n, 3 * (num_future_data + 1)), f)
+    for k in range(n_paths):
+        m = p == k
+        if m.any():
+            rp = ReferencePath(task, k, path_list=path_list)
+            trk[m] = rp.tracking_error_vector(obs[m, 3], obs[m, 4], obs[m, 5], obs[m, 0], num_future_data)
+    obs[:, 6:6 + trk.shape[1]] = trk
+    x, y = obs[:, 3], obs[:, 4]
+    off = 6 + trk.shape[1]
+    for j in range(V):
+        a, b = block(1 + 2 * j), block(2 + 2 * j)
+        near = (a[:, 0] & np.uint32(0xFFFF)) < np.uint32(6554)
+        quad = (a[:, 0] >> np.uint32(16)) & np.uint32(3)
+        u1, u2, u3 = _u01_24(a[:, 1]), _u01_24(a[:, 2]), _u01_24(a[:, 3])
+        vx = np.where(near, x + (u1 * f(16.) - f(8.)), u1 * f(130.) - f(65.)).astype(f)
+        vy = np.where(near, y + (u2 * f(16.) - f(8.)), u2 * f(130.) - f(65.)).astype(f)
+        dd = _sq(vx - x) + _sq(vy - y)
+        vx = np.where(dd < f(36.), vx + f(30.), vx).astype(f)
+        s4 = ((_u01_24(b[:, 0]) + _u01_24(b[:, 1])) + _u01_24(b[:, 2])) + _u01_24(b[:, 3])
+        base = np.choose(quad, [f(0.), f(90.), f(180.), f(-90.)]).astype(f)
+        vphi = base + f(10.) * ((s4 - f(2.)) * f(1.73205077648162842))
+        vphi = np.where(vphi > f(180.), vphi - f(360.), vphi).astype(f)
+        vphi = np.where(vphi <= f(-180.), vphi + f(360.), vphi).astype(f)
+        obs[:, off + 4 * j] = vx
+        obs[:, off + 4 * j + 1] = vy
+        obs[:, off + 4 * j + 2] = f(8.) * u3
+        obs[:, off + 4 * j + 3] = vphi
+    virtual_red = _u01_24(r[:, 3]) > f(0.9)                                    # endtoend.py:120-124
+    return obs, p.astype(np.int32), virtual_red

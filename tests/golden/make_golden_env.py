@@ -16,6 +16,7 @@ methods read; the methods themselves run unmodified:
   CrossroadEnd2end._judge_done (+ the five predicates)  E2E:200-256
   Traffic.collision_check                               traffic.py:263-295
   CrossroadEnd2end._construct_veh_vector_short          E2E:340-464
+  CrossroadEnd2end._reset_init_state                    E2E:472-499
 
 Output: tests/golden/env_<task>.npz (inputs and outputs of those calls, one row per sample).
 """
@@ -139,6 +140,19 @@ def main():
             sel_out.append(env._construct_veh_vector_short())
         out.update(sel_veh=sel_veh, sel_cls=sel_cls, sel_ego=sel_ego, sel_light=sel_light,
                    sel_virtual=sel_virtual, sel_out=np.array(sel_out, np.float32))
+        # ---- _reset_init_state (E2E:472-499): the two np.random.random() draws replayed by seed ----
+        K = 300
+        rst_u, rst_ego, rst_path = np.zeros((K, 2)), np.zeros((K, 6), np.float32), np.zeros(K, np.int64)
+        for i in range(K):
+            k = i % 3
+            env.ref_path = dm.ReferencePath(task, k)
+            np.random.seed(1000 + i)
+            rst_u[i] = np.random.random(), np.random.random()
+            np.random.seed(1000 + i)
+            ego = env._reset_init_state()['ego']
+            rst_ego[i] = [ego['v_x'], ego['v_y'], ego['r'], float(ego['x']), float(ego['y']), float(ego['phi'])]
+            rst_path[i] = k
+        out.update(reset_u=rst_u, reset_ego=rst_ego, reset_path=rst_path)
         np.savez_compressed(os.path.join(HERE, 'env_%s.npz' % task), **out)
         print(task, 'done codes', np.bincount(out['done_code'], minlength=7))
 

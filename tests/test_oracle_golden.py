@@ -203,3 +203,53 @@ def test_vehicle_selection_against_reference_method(task):
         got = orc.select_interested_vehicles(g['sel_veh'][i], g['sel_cls'][i], g['sel_ego'][i, 0], g['sel_ego'][i, 1],
                                              task, int(g['sel_light'][i]), bool(g['sel_virtual'][i]))
         _same(got, g['sel_out'][i], 'scene %d' % i)
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_reset_init_state_against_reference_method(task, golden_task):
+    """oracle.reset_init_state == the UNMODIFIED CrossroadEnd2end._reset_init_state (E2E:472-499) fed the
+    same two np.random.random() draws (make_golden_env.py replays them by seed)."""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, 'env_%s.npz' % task), allow_pickle=False))
+    paths = golden_paths(golden_task(task))
+    for u, ego, k in zip(g['reset_u'], g['reset_ego'], g['reset_path']):
+        _same(orc.reset_init_state(task, paths[int(k)], float(u[0]), float(u[1])), ego, 'reset ego')
+    idx = (g['reset_u'][:, 0] * orc.RESET_SPAN[task]).astype(int) + 700
+    assert idx.min() >= 700 and idx.max() < 700 + orc.RESET_SPAN[task]
+
+
+def test_philox_known_answers():
+    """Random123's known-answer vectors for Philox4x32-10 (kat_vectors: philox4x32 10)."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for c, k, want in kat:
+        got = orc.philox4x32_10(np.array([c], np.uint32), np.array([k], np.uint32))[0]
+        assert tuple(int(x) for x in got) == want
+
+
+def test_env_reset_rows_distribution():
+    """The restated device reset: ego on a waypoint inside the reference's start window with v in [0, 8),
+    zero tracking error up to the path's own granularity, collision-free start, deterministic in
+    (seed, row, episode) and independent of which other rows are drawn with it."""
+    task = 'left'
+    paths = orc.construct_ref_paths(task)[0]
+    rows = np.arange(2000)
+    obs, ref, red = orc.env_reset_rows(1234, rows, np.zeros(2000, int), task, paths, 8)
+    assert obs.dtype == np.float32 and obs.shape == (2000, 41) and set(np.unique(ref)) == {0, 1, 2}
+    assert (obs[:, 0] >= 0).all() and (obs[:, 0] < 8).all() and (obs[:, 1:3] == 0).all()
+    assert abs(obs[:, 0].mean() - 4.0) < 0.2 and 0.05 < red.mean() < 0.15
+    assert np.abs(obs[:, 6]).max() < 0.1          # the projection lands on every 10th waypoint (DM:704-714)
+    assert (obs[:, 8] == obs[:, 0] - np.float32(8)).all()
+    veh = obs[:, 9:].reshape(2000, 8, 4)
+    d = np.hypot(veh[:, :, 0] - obs[:, None, 3], veh[:, :, 1] - obs[:, None, 4])
+    assert d.min() >= 6.0 - 1e-3 and (veh[:, :, 2] >= 0).all() and (veh[:, :, 2] < 8).all()
+    assert (veh[:, :, 3] > -180).all() and (veh[:, :, 3] <= 180).all()
+    sub = np.array([5, 77, 1999])
+    o2, r2, _ = orc.env_reset_rows(1234, sub, np.zeros(3, int), task, paths, 8)
+    _same(o2, obs[sub])
+    assert (r2 == ref[sub]).all()
+    o3, _, _ = orc.env_reset_rows(1234, sub, np.ones(3, int), task, paths, 8)
+    assert not np.array_equal(o3, o2)

@@ -43,18 +43,22 @@ def graph(task, B, V, tma):
 
 def main():
     reps = int(os.environ.get('AB_REPS', '15'))
+    only_tma = os.environ.get('AB_TMA_ONLY') == '1'          # one column: compare builds across processes
+    cfgs = [('left', 65536, 32), ('left', 131072, 32), ('left', 524288, 32), ('left', 65536, 8),
+            ('straight', 65536, 9), ('right', 65536, 5), ('left', 4096, 32)]
+    if os.environ.get('AB_CONFIGS'):
+        cfgs = [cfgs[int(i)] for i in os.environ['AB_CONFIGS'].split(',')]
     print('# k_model_step_pair (TMA) vs k_model_step (cp.async), %s, lib %s\n' % (torch.cuda.get_device_name(0),
                                                                                  os.path.basename(_lib.LIB_PATH)))
     print('| config | TMA us/launch | frac | cp.async us/launch | frac | speed-up |\n|---|---|---|---|---|---|')
-    for task, B, V in [('left', 65536, 32), ('left', 131072, 32), ('left', 524288, 32), ('left', 65536, 8),
-                       ('straight', 65536, 9), ('right', 65536, 5), ('left', 4096, 32)]:
-        gs = {t: graph(task, B, V, t) for t in (True, False)}
+    for task, B, V in cfgs:
+        gs = {t: graph(task, B, V, t) for t in ((True,) if only_tma else (True, False))}
         for g in gs.values():
             for _ in range(3):
                 g.run()
-        ts = {True: [], False: []}
+        ts = {t: [] for t in gs}
         for _ in range(reps):
-            for t in (True, False):
+            for t in gs:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 flush.zero_()
                 a.record()
@@ -65,8 +69,11 @@ def main():
         D = 9 + 4 * V
         med = {t: float(np.median(ts[t])) for t in ts}
         frac = {t: (8 * D + 32) * B / (med[t] * 1e-6) / 1e9 / PEAK for t in ts}
-        print('| %s B=%d V=%d | %.2f | %.3f | %.2f | %.3f | %.3f |' % (task, B, V, med[True], frac[True], med[False],
-                                                                      frac[False], med[False] / med[True]))
+        if only_tma:
+            print('| %s B=%d V=%d | %.2f | %.3f | | | |' % (task, B, V, med[True], frac[True]))
+        else:
+            print('| %s B=%d V=%d | %.2f | %.3f | %.2f | %.3f | %.3f |' % (task, B, V, med[True], frac[True], med[False],
+                                                                          frac[False], med[False] / med[True]))
         del gs
         torch.cuda.empty_cache()
 

@@ -34,7 +34,7 @@ b = padded_rows(B, D, 9)
 a.copy_(torch.as_tensor(obs_h, device='cuda'))
 act = torch.as_tensor(syn.make_actions(rng, 1, B)[0], device='cuda')
 out5 = torch.empty((5, B), device='cuda')
-NW = 296 * 14
+NW = 296 * 14          # = 148 * 28
 trace = torch.zeros((NW, 16), dtype=torch.int64, device='cuda')
 lib = _lib.load()
 flush = torch.empty(512 << 20, dtype=torch.uint8, device='cuda')
@@ -54,7 +54,9 @@ t = trace.cpu().numpy()
 used = t[:, 14] != 0
 t = t[used]
 sm = t[:, 15]
-role = (np.nonzero(used)[0] % 14) & 1
+W = int(os.environ.get('TRACE_WARPS', '28'))         # warps per block of the traced build
+w = np.nonzero(used)[0] % W
+role = ((w ^ (w >> 2)) & 1) if os.environ.get('TRACE_PLAIN_ROLES') != '1' else (w & 1)
 names = {1: 'prologue', 2: 'griddep wait', 3: 'ego loads+sincos', 4: 'ego phase', 5: 'chunk0 wait', 6: 'chunk0', 7: 'chunk1 wait',
          8: 'chunk1', 9: 'chunk2 wait', 10: 'chunk2', 11: 'chunk3 wait', 12: 'chunk3', 13: 'flush', 14: 'exchange+out'}
 t0 = np.zeros_like(t[:, 0])
