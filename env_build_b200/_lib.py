@@ -130,9 +130,10 @@ def make_turn_classes(classes):
     return t
 
 
-def set_tma(enable):
-    """See ce2e_set_tma in include/ce2e.h (on by default).  Returns the previous setting."""
-    return bool(load().ce2e_set_tma(int(bool(enable))))
+def set_tma(mode):
+    """See ce2e_set_tma in include/ce2e.h: False / 0 cp.async kernel, True / 1 TMA kernel (default),
+    2 / 3 TMA kernel with the overlapped / balanced work split forced.  Returns the previous mode."""
+    return int(load().ce2e_set_tma(int(mode)))
 
 
 def set_fast_trig(enable):

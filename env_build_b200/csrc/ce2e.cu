@@ -40,7 +40,9 @@ bool g_use_pdl = getenv("CE2E_NO_PDL") == nullptr;
 bool g_fast_trig = false;
 // A/B switch: ego columns through TMA boxes too (bit 0: loads, bit 1: stores); CE2E_EGO_TMA=0..3
 int g_ego_tma = getenv("CE2E_NO_EGO_TMA") ? 0 : (getenv("CE2E_EGO_TMA") ? atoi(getenv("CE2E_EGO_TMA")) : 3);
-bool g_use_tma = getenv("CE2E_NO_TMA") == nullptr;   // warp-pair TMA kernel for the fused step (ce2e_set_tma)
+// warp-pair TMA kernel for the fused step (ce2e_set_tma): 0 off, 1 on (work split chosen by batch size),
+// 2 / 3 on with the overlapped / balanced split forced
+int g_use_tma = getenv("CE2E_NO_TMA") ? 0 : 1;
 
 int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -690,17 +692,26 @@ int launch_model_step_pair(const StepParams &P, const DeviceInfo *di, cudaStream
             PP.ego_tma_out = vehicle_tensor_map(P.obs_out + P.ld_out - 7, P.ld_out, P.B - 1, 4, &PP.tm_ego_out, true);
     }
     const bool fast = g_fast_trig;
-    void (*kern)(const PairParams) = fast ? k_model_step_pair<true> : k_model_step_pair<false>;
-    static std::atomic<bool> smem_set[64][2];
+    const int64_t n_tiles = (P.B + PAIR_ROWS - 1) / PAIR_ROWS;
+    const int64_t max_blocks = PAIR_BLOCKS_PER_SM * (int64_t)di->sms;
+    // Up to two tiles per pair (B <= 2 * 32 * 14 * SMs = 132608 rows on a B200): the reward warp runs its
+    // vehicle chunks under the dynamics warp's latency chain (f_xu -> candidate cell -> scan -> tracking),
+    // which measured 3-5 % faster than splitting that chain evenly (15.16 vs 15.65 us at B = 65536, 30.3 vs
+    // 31.8 us at 131072).  Many tiles per pair: the even split (BAL) keeps both warps of a pair in step and
+    // measured 6 % faster (117.0 vs 124.6 us at B = 524288).  CE2E_PAIR_BAL=0/1 forces.
+    static const int env_bal = getenv("CE2E_PAIR_BAL") ? atoi(getenv("CE2E_PAIR_BAL")) : -1;
+    const int force_bal = g_use_tma >= 2 ? g_use_tma - 2 : env_bal;
+    const bool bal = force_bal >= 0 ? force_bal != 0 : n_tiles > 2 * max_blocks * PAIR_PAIRS;
+    void (*kern)(const PairParams) = fast ? (bal ? k_model_step_pair<true, true> : k_model_step_pair<true, false>)
+                                          : (bal ? k_model_step_pair<false, true> : k_model_step_pair<false, false>);
+    static std::atomic<bool> smem_set[64][4];
     int dev = 0;
     CE2E_CUDA(cudaGetDevice(&dev));
-    std::atomic<bool> &set = smem_set[dev & 63][fast ? 1 : 0];
+    std::atomic<bool> &set = smem_set[dev & 63][(fast ? 2 : 0) + (bal ? 1 : 0)];
     if (!set.load(std::memory_order_acquire)) {
         CE2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di->max_smem_optin));
         set.store(true, std::memory_order_release);
     }
-    const int64_t n_tiles = (P.B + PAIR_ROWS - 1) / PAIR_ROWS;
-    const int64_t max_blocks = PAIR_BLOCKS_PER_SM * (int64_t)di->sms;
     const int64_t blocks = n_tiles < max_blocks ? n_tiles : max_blocks;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1649,9 +1660,9 @@ int ce2e_set_fast_trig(int enable) {
     g_fast_trig = enable != 0;
     return old;
 }
-int ce2e_set_tma(int enable) {
+int ce2e_set_tma(int mode) {
     const int old = g_use_tma;
-    g_use_tma = enable != 0;
+    g_use_tma = mode < 0 ? 0 : (mode > 3 ? 1 : mode);
     return old;
 }
 int ce2e_last_step_kernel(void) { return g_last_step_kernel; }

@@ -66,13 +66,14 @@ const char *ce2e_last_error(void);
  * unchanged.  Returns the previous setting.                                                   */
 int ce2e_set_fast_trig(int enable);
 
-/* Process-wide option, default 1 (environment CE2E_NO_TMA=1 starts with 0).  enable != 0: the fused
+/* Process-wide option, default 1 (environment CE2E_NO_TMA=1 starts with 0).  mode != 0: the fused
  * step (ce2e_rollout_step / ce2e_env_step; EnvironmentModel.rollout_out, DM:118-126) runs the
- * warp-pair kernel that streams the vehicle block with TMA tensor-map copies whenever the vehicle block
- * of obs_in and obs_out is 16-byte aligned with ld % 4 == 0, V_in == V_out >= 1 and B >= 32; otherwise,
- * and with enable == 0, the cp.async kernel runs.  Both give bit-identical results.  Returns the
- * previous setting.                                                                            */
-int ce2e_set_tma(int enable);
+ * warp-pair kernel that streams the vehicle block and the ego columns with TMA tensor-map copies
+ * whenever the vehicle block of obs_in and obs_out is 16-byte aligned with ld % 4 == 0, V_in == V_out
+ * >= 1 and B >= 32; otherwise, and with mode == 0, the cp.async kernel runs.  mode 1 picks the pair's
+ * work split from the batch size, 2 / 3 force the overlapped / the balanced split (tests, A/B runs).
+ * All variants give bit-identical results.  Returns the previous mode.                          */
+int ce2e_set_tma(int mode);
 
 /* Which kernel the calling thread's last fused-step launch (rollout_out, DM:118-126) used: 0 none
  * yet, 1 k_model_step (cp.async staging), 2 k_model_step_pair (TMA tensor-map staging).

@@ -233,3 +233,104 @@ def test_judge_done_tiled_equals_scalar(e2e, V):
         codes.append(done.cpu().numpy())
     assert (codes[0] >= 0).all() and (codes[0] == codes[1]).all()
     assert (codes[0] == 1).sum() > 0 or V < 5                    # collisions present
+
+
+# ------------------------------------------------------------------------------------------
+# on-device reset (ce2e_env_reset), graph stepping, set_traj
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('task,V', [('left', 8), ('straight', 9), ('right', 5), ('left', 32)])
+def test_device_reset_matches_oracle(e2e, task, V):
+    """reset() on the device against the NumPy restatement of the same draws (oracle.env_reset_rows, whose
+    ego part is pinned to the unmodified _reset_init_state): every column bit for bit."""
+    B = 3000
+    env = e2e.CrossroadEnd2end(task, num_envs=B, veh_num=V)
+    env.seed(20210318)
+    obs = env.reset().numpy()
+    want, ref, red = orc.env_reset_rows(20210318, np.arange(B), np.zeros(B, int), task, env.ref_path.path_list, V)
+    assert (env.ref_indexes.cpu().numpy() == ref).all() and set(np.unique(ref)) == {0, 1, 2}
+    assert np.array_equal(obs.view(np.int32), want.view(np.int32)), np.argwhere(obs != want)[:5]
+    assert (env._bufs['red'].cpu().numpy().astype(bool) == red).all()
+    # a second reset is the next episode of every row
+    obs2 = env.reset().numpy()
+    want2, _, _ = orc.env_reset_rows(20210318, np.arange(B), np.ones(B, int), task, env.ref_path.path_list, V)
+    assert np.array_equal(obs2.view(np.int32), want2.view(np.int32))
+    # pinned path
+    obs3 = env.reset(ref_index=2).numpy()
+    want3, ref3, _ = orc.env_reset_rows(20210318, np.arange(B), np.full(B, 2), task, env.ref_path.path_list, V, fixed_path=2)
+    assert (ref3 == 2).all() and np.array_equal(obs3.view(np.int32), want3.view(np.int32))
+
+
+def test_auto_reset_on_device_in_a_graph(e2e):
+    """auto_reset with use_graph=True: step = fused model step + done kernel + reset kernel replayed as one
+    CUDA graph; identical to the eager path, rows that finish are replaced by the oracle's reset rows of
+    their next episode, and nothing synchronises with the host (no nonzero / item in step)."""
+    task, B, V = 'left', 4096, 8
+    envs = [e2e.CrossroadEnd2end(task, num_envs=B, veh_num=V, auto_reset=True, use_graph=g, reward_info=False)
+            for g in (True, False)]
+    for env in envs:
+        env.seed(7)
+        env.reset()
+    rng = np.random.default_rng(0)
+    episodes = np.zeros(B, int)
+    n_done = 0
+    for t in range(40):
+        act = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+        outs = [env.step(act) for env in envs]
+        o_g, o_e = outs[0][0].numpy(), outs[1][0].numpy()
+        assert np.array_equal(o_g.view(np.int32), o_e.view(np.int32)), t
+        assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+        done = outs[0][2].cpu().numpy()
+        n_done += int(done.sum())
+        episodes += done
+        rows = np.flatnonzero(done)
+        if len(rows):
+            want, ref, _ = orc.env_reset_rows(7, rows, episodes[rows], task, envs[0].ref_path.path_list, V)
+            assert np.array_equal(o_g[rows].view(np.int32), want.view(np.int32)), (t, rows[:5])
+            assert (envs[0].ref_indexes.cpu().numpy()[rows] == ref).all()
+        assert 'reward_info' not in outs[0][3]
+    assert n_done > 50
+    assert (envs[0]._bufs['episode'].cpu().numpy() == episodes + 1).all()
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_set_traj_reprojects_tracking(e2e, task):
+    """The reference's decision pattern `env.set_traj(path); env._get_obs()` (hier_decision.py:115-124):
+    tracking columns re-projected onto the new path, and the next step keeps following it."""
+    from env_build_b200.dynamics_and_models import ReferencePath
+    env = e2e.CrossroadEnd2end(task)
+    env.seed(11)
+    obs0 = env.reset().copy()
+    paths = env.ref_path.path_list
+    for k in range(3):
+        traj = ReferencePath(task, k)
+        env.set_traj(traj)
+        got = env._get_obs()
+        rp = orc.ReferencePath(task, k, path_list=paths)
+        want = rp.tracking_error_vector(obs0[3:4], obs0[4:5], obs0[5:6], obs0[0:1], 0)[0]
+        assert np.array_equal(got[6:9].view(np.int32), want.view(np.int32)), k
+        assert np.array_equal(got[:6], obs0[:6]) and np.array_equal(got[9:], obs0[9:])
+        assert int(env.ref_indexes[0]) == k
+    act = np.array([0.1, 0.2], np.float32)
+    nxt, _, _, info = env.step(act)
+    want_obs, _, _, _ = orc.gym_env_step(np.concatenate([obs0[:6], want, obs0[9:]])[None], act[None], task,
+                                         np.array([2], np.int32), paths, orc.VEHICLE_MODE_LIST[task])
+    assert info['ref_index'] == 2
+    assert np.allclose(nxt[:6], want_obs[0, :6], rtol=1e-5, atol=1e-5)
+    assert np.allclose(nxt[6:9], want_obs[0, 6:9], rtol=1e-5, atol=2e-5)
+
+
+def test_assigned_obs_is_adopted(e2e):
+    """env.obs / env.ref_indexes are plain attributes in the reference; assigning them must take effect."""
+    from env_build_b200 import synthetic as syn
+    rng = np.random.default_rng(1)
+    task, B, V = 'left', 512, 8
+    env = e2e.CrossroadEnd2end(task, num_envs=B)
+    env.reset()
+    ref = syn.make_ref_indexes(rng, B)
+    obs = syn.make_obs(rng, B, task, V, env.ref_path.path_list, ref)
+    act = syn.make_actions(rng, 1, B)[0]
+    env.obs = env.env_model._adopt(obs)
+    env.ref_indexes = torch.as_tensor(ref, device='cuda')
+    got = env.step(act)[0].numpy()
+    want = orc.gym_env_step(obs, act, task, ref, env.ref_path.path_list, orc.VEHICLE_MODE_LIST[task])[0]
+    assert np.allclose(got[:, :6], want[:, :6], rtol=1e-5, atol=1e-5)

@@ -839,7 +839,7 @@ def test_tma_kernel_equals_cp_async_kernel(dm, task, V, n, mode):
         obs = syn.make_obs(rng, B, task, V, model.ref_path.path_list, ref if mode == 'training' else 1, n)
         act = syn.make_actions(rng, 2, B)
         res = {}
-        for tma in (True, False):
+        for tma in (2, 3, 0):                               # overlapped split, balanced split, cp.async kernel
             old = _lib.set_tma(tma)
             try:
                 n0 = _lib.launch_count()
@@ -854,9 +854,10 @@ def test_tma_kernel_equals_cp_async_kernel(dm, task, V, n, mode):
                 assert _lib.launch_count() - n0 == 2
             finally:
                 _lib.set_tma(old)
-        for a, b in zip(res[True], res[False]):
-            for x, y in zip(a, b):
-                bits_equal(x, y)
+        for tma in (2, 3):
+            for a, b in zip(res[tma], res[0]):
+                for x, y in zip(a, b):
+                    bits_equal(x, y)
 
 
 def test_tma_kernel_is_the_default_path(dm):
