@@ -39,7 +39,8 @@ BYTES_PER_ENV_STEP = 8 * D + 32          # obs in+out, action 8, r
 
 
 def workload_config(B, n_gpus):
-    return {'workload': 'EnvironmentModel.rollout_out rollout, BASELINE config #3 per GPU',
+    return {'workload': 'EnvironmentModel.rollout_out rollout, BASELINE config #3 per GPU (weak scaling; the N=8 line '
+                        'also carries config #5 at its stated size under "config5")',
             'task': TASK, 'mode': 'training (per-row ref path of 3)', 'batch_per_gpu': B, 'vehicles': V,
             'obs_dim': D, 'horizon': H, 'global_batch': B * n_gpus,
             'parallelism': 'rows sharded over %d GPU(s), no data-path collective' % n_gpus,
@@ -325,6 +326,58 @@ def run_ours(args):
     h2d = obs.nbytes + ref.nbytes + tape.nbytes
     d2h = h_out5.numel() * 4 + h_final.numel() * 4
 
+    # the same path when the caller consumes what the reference's shield rollouts consume: the per-step
+    # veh2veh4real vector only (hier_decision.py:97, multi_ego.py:197); same H2D, 1/10 of the D2H
+    h_v2v = torch.empty((H, B), dtype=torch.float32).pin_memory()
+
+    def e2e_shield_step():
+        main = torch.cuda.current_stream()
+        st = stage[counter[0] % 2]
+        counter[0] += 1
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(st['free'])
+            st['obs'].copy_(h_obs, non_blocking=True)
+            st['ref'].copy_(h_ref, non_blocking=True)
+            st['tape'].copy_(h_tape, non_blocking=True)
+            st['ready'].record(copy_s)
+        main.wait_event(st['ready'])
+        model.reset(st['obs'], st['ref'])
+        v2v = st['v2v']
+        for t in range(H):
+            v2v[t] = model.rollout_out(st['tape'][t])[4]
+        st['free'].record(main)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            h_v2v.copy_(v2v, non_blocking=True)
+
+    for st_ in stage:
+        st_['v2v'] = torch.empty((H, B), device=dev)
+    sh_runs = sorted(timed(e2e_shield_step, 2 if i == 0 else 1, ke, after=join_streams) for i in range(3))
+    e2e_shield = {'value': world * B * H * ke / (sh_runs[1] / 1e3), 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d,
+                  'd2h_bytes_per_step': h_v2v.numel() * 4,
+                  'note': 'same public-API path, D2H of the per-step veh2veh4real vector only (what the reference\'s '
+                          'safety-shield callers read, hier_decision.py:97); NOT the headline e2e'}
+
+    # what the box's host<->device links give for exactly these transfers, nothing else running: every
+    # rank moves the e2e leg's H2D and D2H bytes concurrently from / to its pinned buffers
+    def bare_copies():
+        st = stage[0]
+        with torch.cuda.stream(copy_s):
+            st['obs'].copy_(h_obs, non_blocking=True)
+            st['ref'].copy_(h_ref, non_blocking=True)
+            st['tape'].copy_(h_tape, non_blocking=True)
+        with torch.cuda.stream(side):
+            h_out5.copy_(d_out5, non_blocking=True)
+            h_final.copy_(st['obs'], non_blocking=True)
+
+    d_out5 = torch.empty((H, 5, B), device=dev)
+    ms_c = timed(bare_copies, 2, ke, after=join_streams)
+    link = {'value': world * B * H * ke / (ms_c / 1e3), 'unit': 'env-steps/s',
+            'h2d_gbs_per_gpu': h2d * ke / (ms_c / 1e3) / 1e9, 'd2h_gbs_per_gpu': d2h * ke / (ms_c / 1e3) / 1e9,
+            'aggregate_gbs': world * (h2d + d2h) * ke / (ms_c / 1e3) / 1e9,
+            'note': 'ceiling of the e2e leg on this box: only its pinned-memory H2D + D2H copies, all %d rank(s) at '
+                    'once, no kernels' % world}
+
     # ---- HBM-bound variant: batch too large for L2 (reported beside the headline, not as it) ----
     extra = {}
     if args.large_batch and world == 1:
@@ -364,32 +417,140 @@ def run_ours(args):
                          'per-step bytes are only actions + the five outputs, so the per-step HBM roofline does '
                          'not apply; results bit-identical to the per-step launches; NOT the headline' % H}
         del rh
+    # ---- the reference's own vehicle counts (EU:21-23, EU:40-42): one launch per step at V = 8 / 9 / 5
+    native = None
+    if world == 1:
+        from env_build_b200 import synthetic as syn
+        from env_build_b200.endtoend_env_utils import VEHICLE_MODE_LIST, VEH_NUM
+        native = {}
+        for task_n in ('left', 'straight', 'right'):
+            Vn = VEH_NUM[task_n]
+            Dn = 9 + 4 * Vn
+            rng_n = np.random.default_rng(5)
+            mn = EnvironmentModel(task_n, 0, mode='training', veh_mode_list=VEHICLE_MODE_LIST[task_n])
+            ref_n = syn.make_ref_indexes(rng_n, B)
+            rn = RolloutGraph(mn, B, Vn, H)
+            rn.load(syn.make_obs(rng_n, B, task_n, Vn, mn.ref_path.path_list, ref_n), ref_n, syn.make_actions(rng_n, H, B))
+            ms_n = timed(rn.run, 3, K)
+            us_n = 1e3 * ms_n / (K * H)
+            native[task_n] = {'vehicles': Vn, 'obs_dim': Dn, 'value': B * H * K / (ms_n / 1e3), 'launch_us': us_n,
+                              'bytes_per_env_step': 8 * Dn + 32,
+                              'frac': (8 * Dn + 32) * B / (us_n * 1e-6) / 1e9 / peak}
+            del rn, mn
+        native['note'] = 'same kernel and batch at the task\'s native vehicle count; %d rows x 8D+32 bytes is %s of ' \
+                         'HBM time, so these launches are bound by per-launch latency, not bandwidth' % (B, '3-4 us')
+    # ---- f-1: the batched SUMO-free CrossroadEnd2end, one step = fused model step + done kernel + on-device
+    # auto-reset, replayed as one CUDA graph (no host synchronisation)
+    env_rec = None
+    if world == 1:
+        from env_build_b200.endtoend import CrossroadEnd2end
+        env = CrossroadEnd2end(TASK, num_envs=B, veh_num=V, auto_reset=True, use_graph=True, reward_info=False)
+        env.seed(1)
+        env.reset()
+        a_env = torch.zeros((B, 2), device=dev)
+        for _ in range(4):
+            env.step(a_env)
+        n_env = 100
+        ms_env = timed(lambda: [env.step(a_env) for _ in range(n_env)], 1, 3)
+        env_rec = {'us_per_step': 1e3 * ms_env / (3 * n_env), 'value': B * 3 * n_env / (ms_env / 1e3), 'unit': 'env-steps/s',
+                   'note': 'CrossroadEnd2end(num_envs=%d, veh_num=%d, auto_reset=True, use_graph=True).step(): three '
+                           'kernels per step (k_model_step_pair, k_env_done, k_env_reset) in one graph replay, Python '
+                           'call included' % (B, V)}
+        del env
     # ---- N > 1: the batch lives on rank 0; NCCL scatters the row blocks and gathers the returns
-    sharded = None
+    sharded, config5 = None, None
     if world > 1:
         from env_build_b200.parallel import ShardedRollout
-        Bg = world * B
-        sr = ShardedRollout(lambda b: RolloutGraph(model, b, V, H), Bg, D, H, dev)
-        if rank == 0:
-            _, g_obs, g_ref, g_tape = make_inputs(Bg, 4242)
-            full = [torch.from_numpy(g_obs).to(dev), torch.from_numpy(g_ref).to(dev), torch.from_numpy(g_tape).to(dev)]
-        else:
-            full = [None, None, None]
-        ret = {}
 
-        def sharded_step():
-            sr.scatter(*full)
-            sr.run()
-            ret['r'] = sr.gather_returns()
+        def sharded_leg(Bper, check):
+            """Global batch of world * Bper rows resident on rank 0 in scatter-ready layout; per rollout: NCCL
+            scatter (views of it -> the ranks' static buffers), H-step rollout on every rank, NCCL gather of the
+            per-row returns.  Two buffer sets per rank: the next rollout's scatter runs on a side stream under
+            the current rollout's kernels."""
+            Bg = world * Bper
+            sr = ShardedRollout(lambda b: RolloutGraph(model, b, V, H), Bg, D, H, dev, slots=2)
+            staged = None
+            if rank == 0:
+                _, g_obs, g_ref, g_tape = make_inputs(Bg, 4242)
+                staged = sr.stage(g_obs, g_ref, g_tape)
+            for r_ in sr.runners:
+                r_.run()                                  # capture the graphs before any timing
+            comm = torch.cuda.Stream()
+            ready = [torch.cuda.Event() for _ in range(2)]
+            done = [torch.cuda.Event() for _ in range(2)]
+            ret = {}
+            state = {'i': 0}
 
-        ks = max(3, min(K, 10))
-        ms_s = timed(sharded_step, 2, ks)
-        sharded = {'value': Bg * H * ks / (ms_s / 1e3), 'unit': 'env-steps/s', 'ms_per_step': ms_s / ks,
-                   'scatter_bytes_per_step': int(Bg * (D * 4 + 4 + H * 8)), 'gather_bytes_per_step': int(Bg * 20),
-                   'note': 'global batch of %d rows resident on rank 0: NCCL scatter of observations, path indexes '
-                           'and the action tape, %d-step rollout on every rank, NCCL gather of the per-row returns '
-                           '(sum over steps of the five outputs)' % (Bg, H)}
-        del sr, full
+            def issue_scatter(slot):
+                with torch.cuda.stream(comm):
+                    comm.wait_event(done[slot])           # the rollout that last used this buffer set is finished
+                    sr.scatter_staged(staged, slot=slot)
+                    ready[slot].record(comm)
+
+            def step():
+                main = torch.cuda.current_stream()
+                i = state['i']
+                slot = i % 2
+                if i == 0:
+                    issue_scatter(0)
+                issue_scatter(1 - slot)                   # next rollout's inputs travel while this one computes
+                main.wait_event(ready[slot])
+                sr.run(slot=slot)
+                done[slot].record(main)
+                ret['r'] = sr.gather_returns(slot=slot)
+                state['i'] = i + 1
+
+            for e_ in done:
+                e_.record(torch.cuda.current_stream())
+            ks = max(3, min(K, 10))
+            ms_s = timed(step, 2, ks, after=lambda: torch.cuda.current_stream().wait_stream(comm))
+            scatter_bytes = int(Bg * (sr.runner.obs0.stride(0) * 4 + 4 + H * 8))
+            out = {'value': Bg * H * ks / (ms_s / 1e3), 'unit': 'env-steps/s', 'ms_per_step': ms_s / ks,
+                   'global_batch': Bg, 'scatter_bytes_per_step': scatter_bytes, 'gather_bytes_per_step': int(Bg * 20),
+                   'root_egress_gbs': scatter_bytes * (world - 1) / world / (ms_s / ks / 1e3) / 1e9,
+                   'nvlink_per_direction_gbs': {'nominal': 900, 'measured_peer_copy': 770}}
+            if check:
+                # driver-side NCCL correctness: the gathered returns against a local rollout of the same rows
+                torch.cuda.synchronize()
+                verdict = 'n/a'
+                if rank == 0:
+                    got = ret['r']
+                    ok = True
+                    one = RolloutGraph(model, Bper, V, H)
+                    _, g_obs, g_ref, g_tape = make_inputs(Bg, 4242)
+                    for r_ in range(world):
+                        lo, hi = r_ * Bper, (r_ + 1) * Bper
+                        one.load(g_obs[lo:hi], g_ref[lo:hi], g_tape[:, lo:hi])
+                        one.run()
+                        ok = ok and bool(torch.equal(one.out5.sum(0).t().contiguous(), got[lo:hi]))
+                    verdict = 'bit-identical' if ok else 'MISMATCH'
+                    del one
+                out['sharded_check'] = verdict
+            del sr, staged
+            return out
+
+        sharded = sharded_leg(B, True)
+        sharded['vs_exchange_free'] = sharded['value'] / value
+        sharded['note'] = ('global batch resident on rank 0: NCCL scatter of observations (padded rows), path indexes and '
+                           'the action tape as views of the staged batch, %d-step rollout on every rank, NCCL gather of '
+                           'the per-row returns (sum over steps of the five outputs); the scatter of rollout i+1 overlaps '
+                           'the kernels of rollout i' % H)
+        if world == 8:
+            # ---- BASELINE config #5 at its stated size: B = 1 048 576 over 8 GPUs (131 072 rows per GPU)
+            B5 = 131072
+            _, obs5, ref5, tape5 = make_inputs(B5, 20210315 * 1000 + rank)
+            r5 = RolloutGraph(model, B5, V, H)
+            r5.load(obs5, ref5, tape5)
+            ms_5 = timed(r5.run, 3, max(3, min(K, 10)))
+            k5 = max(3, min(K, 10))
+            us_5 = 1e3 * ms_5 / (k5 * H)
+            del r5
+            config5 = {'workload': 'BASELINE config #5: batch=1048576 full model rollout horizon=25 on 8xB200',
+                       'global_batch': world * B5, 'batch_per_gpu': B5, 'value': world * B5 * H * k5 / (ms_5 / 1e3),
+                       'unit': 'env-steps/s', 'launch_us': us_5,
+                       'frac_per_gpu': BYTES_PER_ENV_STEP * B5 / (us_5 * 1e-6) / 1e9 / peak,
+                       'with_exchange': sharded_leg(B5, False)}
+            config5['with_exchange']['vs_exchange_free'] = config5['with_exchange']['value'] / config5['value']
     t1 = time.perf_counter()
     clocks = sampler.stop(t0, t1) if sampler else None     # sampled over all GPU legs above
     cpu = None
@@ -416,15 +577,18 @@ def run_ours(args):
                         'd2h_bytes_per_step': d2h, 'steps': ke, 'timing': 'one CUDA-event pair around all steps; H2D, kernels and D2H run on '
                         'three streams, all joined before the end event; median of three such runs',
                         'runs': [world * B * H * ke / (m / 1e3) for m in e2e_runs],
+                        'shield_outputs': e2e_shield, 'link_ceiling': link,
+                        'vs_link_ceiling': e2e_value / link['value'],
                         'path': 'EnvironmentModel.reset + %d x rollout_out; observations, path indexes and the action tape come from pinned host buffers, all per-step outputs and the final observations go back to pinned host buffers' % H},
                 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                              'frac': achieved / peak, 'traffic': ncu_traffic(), 'peak_source': peak_src,
-                             'kernel': 'k_model_step<REW=1,NEXT=1>', 'launch_us': launch_us,
+                             'kernel': 'k_model_step_pair (TMA tensor-map staging; the fused rollout_out step)',
+                             'launch_us': launch_us,
                              'bytes_per_launch': BYTES_PER_ENV_STEP * B,
                              'note': 'algorithmic bytes (8*D+32)*B per launch; at this batch the obs ping-pong '
                                      'fits L2, see large_batch for the HBM-bound rate'},
-                'large_batch': extra or None, 'fast_trig_option': fast, 'horizon_fused_mode': fused,
-                'sharded_from_rank0': sharded,
+                'large_batch': extra or None, 'native_v': native, 'env_step': env_rec, 'fast_trig_option': fast,
+                'horizon_fused_mode': fused, 'sharded_from_rank0': sharded, 'config5': config5,
                 'cpu_baseline': cpu}
         emit(line)
     if world > 1:

@@ -29,6 +29,15 @@ class TurnClasses(ctypes.Structure):
     _fields_ = [('tc', ctypes.c_int8 * MAX_VEH)]
 
 
+class Config(ctypes.Structure):
+    """ce2e_config of include/ce2e.h."""
+    _fields_ = [('L', ctypes.c_double), ('W', ctypes.c_double), ('lane_width', ctypes.c_double),
+                ('lane_number', ctypes.c_int), ('crossroad_size', ctypes.c_double), ('expected_v', ctypes.c_double),
+                ('w_devi_v', ctypes.c_double), ('w_devi_y', ctypes.c_double), ('w_devi_phi', ctypes.c_double),
+                ('w_punish_yaw_rate', ctypes.c_double), ('w_punish_steer', ctypes.c_double),
+                ('w_punish_a_x', ctypes.c_double)]
+
+
 _c = ctypes
 _vp, _i, _i64, _d = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double
 
@@ -37,6 +46,8 @@ SIGNATURES = {
     'ce2e_version': (_i, []),
     'ce2e_last_error': (_c.c_char_p, []),
     'ce2e_launch_count': (_i64, []),
+    'ce2e_config_set': (_i, [_c.POINTER(Config)]),
+    'ce2e_config_get': (_i, [_c.POINTER(Config)]),
     'ce2e_set_fast_trig': (_i, [_i]),
     'ce2e_set_tma': (_i, [_i]),
     'ce2e_last_step_kernel': (_i, []),

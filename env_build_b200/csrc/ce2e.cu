@@ -35,6 +35,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int64_t g_launches = 0;
+ce2e_config g_config = {4.8, 2.0, 3.75, 3, 50.0, 8.0, 0.05, 0.8, 30.0, 0.02, 5.0, 0.05};
 thread_local int g_last_step_kernel = 0;   // 1: k_model_step (cp.async), 2: k_model_step_pair (TMA)
 bool g_use_pdl = getenv("CE2E_NO_PDL") == nullptr;
 bool g_fast_trig = false;
@@ -465,17 +466,17 @@ k_model_step(const __grid_constant__ StepParams P) {
             const float devi_y = -sq(e9[6]);
             const float devi_phi = -sq(deg2rad(e9[7]));
             const float devi_v = -sq(e9[8]);
-            rewards = ((((0.05f * devi_v + 0.8f * devi_y) + 30.0f * devi_phi) + 0.02f * punish_yaw) +
-                       5.0f * punish_steer) + 0.05f * punish_a_x;       // DM:297-298
+            rewards = ((((CE2E_K.w_v * devi_v + CE2E_K.w_y * devi_y) + CE2E_K.w_phi * devi_phi) + CE2E_K.w_yaw * punish_yaw) +
+                       CE2E_K.w_steer * punish_steer) + CE2E_K.w_ax * punish_a_x;       // DM:297-298
             road_terms(P.task, ec.fx, ec.fy, v2r_tr, v2r_re);
             road_terms(P.task, ec.rx, ec.ry, v2r_tr, v2r_re);
             if (P.dict16 && valid && h == 0) {
                 float *d = P.dict16 + row;
                 const int64_t B = P.B;
                 d[0] = punish_steer; d[B] = punish_a_x; d[2 * B] = punish_yaw; d[3 * B] = devi_v;
-                d[4 * B] = devi_y; d[5 * B] = devi_phi; d[6 * B] = 5.0f * punish_steer;
-                d[7 * B] = 0.05f * punish_a_x; d[8 * B] = 0.02f * punish_yaw;
-                d[9 * B] = 0.05f * devi_v; d[10 * B] = 0.8f * devi_y; d[11 * B] = 30.0f * devi_phi;
+                d[4 * B] = devi_y; d[5 * B] = devi_phi; d[6 * B] = CE2E_K.w_steer * punish_steer;
+                d[7 * B] = CE2E_K.w_ax * punish_a_x; d[8 * B] = CE2E_K.w_yaw * punish_yaw;
+                d[9 * B] = CE2E_K.w_v * devi_v; d[10 * B] = CE2E_K.w_y * devi_y; d[11 * B] = CE2E_K.w_phi * devi_phi;
             }
         }
         float e9n[9];
@@ -1194,11 +1195,12 @@ __device__ __forceinline__ void road_terms_grad(int task, float px, float py, fl
 __device__ __forceinline__ void pair_grad(float ex, float ey, float px, float py, float w_tr, float w_re,
                                           float &gx, float &gy) {
     // d/dE of hinge^2: 2 (d - thr) (E - P) / d inside the threshold, else 0.  Branch free (few lanes
-    // of a warp are ever inside the gate); 1/d from the special-function unit -- gradients are checked
-    // against float64 autograd at 2e-3, not bit for bit.
+    // of a warp are ever inside the gate).  1/d: the special-function unit's estimate plus one Newton
+    // step (2 FMA), ~1 ulp -- the gradients are checked at 1e-4 against the reference's own autodiff.
     const float dx = ex - px, dy = ey - py;
     const float dd = dx * dx + dy * dy;
-    const float inv_d = rsqrtf(dd);
+    float inv_d = rsqrtf(dd);
+    inv_d = __fmaf_rn(inv_d, __fmaf_rn(-0.5f * dd * inv_d, inv_d, 0.5f), inv_d);
     const float d = dd * inv_d;
     const float k = (w_tr * fminf(d - 3.5f, 0.0f) + w_re * fminf(d - 2.5f, 0.0f)) * (2.0f * inv_d);
     const bool in = dd < 12.25f && dd > 0.0f;
@@ -1256,16 +1258,16 @@ k_model_step_bwd(const __grid_constant__ PathView pv, const __grid_constant__ Gr
     // gradients w.r.t. (vx, vy, r, x, y, phi_deg, steer, a_x) and the tracking columns
     float gvx = 0.f, gvy = 0.f, gr = 0.f, gx = 0.f, gy = 0.f, gphi = 0.f, gsteer = 0.f, gax = 0.f;
     // ---- rewards (DM:198-207, 297-298)
-    const float g_dy = gR * (-1.6f * o[6]);
-    const float g_dphi = gR * (-60.0f * D2R * D2R * o[7]);
-    const float g_dv = gR * (-0.1f * o[8]);
+    const float g_dy = gR * (-(2.0f * CE2E_K.w_y) * o[6]);
+    const float g_dphi = gR * (-(2.0f * CE2E_K.w_phi) * D2R * D2R * o[7]);
+    const float g_dv = gR * (-(2.0f * CE2E_K.w_v) * o[8]);
     // TILED: lane h = 0 takes the reward + penalty terms, lane h = 1 the next-observation terms; the
     // partial gradients are added at the end
     const bool do_rew = !TILED || (lane & 1) == 0, do_next = !TILED || (lane & 1) == 1;
     if (do_rew) {
-        gr += gR * (-0.04f * r);
-        gsteer += gR * (-10.0f * steer);
-        gax += gR * (-0.1f * a_x);
+        gr += gR * (-(2.0f * CE2E_K.w_yaw) * r);
+        gsteer += gR * (-(2.0f * CE2E_K.w_steer) * steer);
+        gax += gR * (-(2.0f * CE2E_K.w_ax) * a_x);
     }
     // ---- collision and road penalties through the ego circle centres (DM:210-295)
     {
@@ -1512,26 +1514,60 @@ struct ResetParams {
     uint32_t seed_lo, seed_hi;
 };
 
-__global__ void k_env_reset(const __grid_constant__ ResetParams R, int32_t *__restrict__ episode,
-                            const int8_t *__restrict__ done, float *__restrict__ obs, int64_t ld,
-                            int32_t *__restrict__ ref_idx, int8_t *__restrict__ virtual_red, int64_t B) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B) return;
-    if (done && done[i] == 0) return;
-    const uint32_t ep = (uint32_t)episode[i];
-    episode[i] = (int32_t)(ep + 1u);
-    const uint32_t i_lo = (uint32_t)i, i_hi = (uint32_t)((uint64_t)i >> 32);
-    const Philox4 r = philox4x32_10(i_lo, i_hi, ep, 0u, R.seed_lo, R.seed_hi);
-    const int p = R.fixed_path >= 0 ? R.fixed_path : (int)(((uint64_t)r.v[0] * (uint32_t)R.pv.n_paths) >> 32);
-    const int L = R.pv.L[p];
-    int idx = (int)(((uint64_t)r.v[1] * (uint32_t)R.span) >> 32) + 700;         // E2E:473-478
-    idx = idx < L ? idx : L - 1;                                                 // indexs2points clamp, DM:727-728
-    const float *tab = R.full[p];
-    const float x = tab[idx], y = tab[L + idx], phi = tab[2 * (size_t)L + idx];
-    const float v = CE2E_EXP_V * u01_24(r.v[2]);                                 // E2E:482
-    float *o = obs + i * ld;
-    o[0] = v; o[1] = 0.0f; o[2] = 0.0f; o[3] = x; o[4] = y; o[5] = phi;
-    {
+// One vehicle slot of a fresh episode (see k_env_reset): draws of Philox blocks 1 + 2 j and 2 + 2 j.
+__device__ __forceinline__ float4 reset_vehicle(uint32_t i_lo, uint32_t i_hi, uint32_t ep, int j, uint32_t k0, uint32_t k1,
+                                                float x, float y) {
+    const Philox4 a = philox4x32_10(i_lo, i_hi, ep, 1u + 2u * (uint32_t)j, k0, k1);
+    const Philox4 b = philox4x32_10(i_lo, i_hi, ep, 2u + 2u * (uint32_t)j, k0, k1);
+    const bool near = (a.v[0] & 0xffffu) < 6554u;
+    const int quad = (int)((a.v[0] >> 16) & 3u);
+    const float u1 = u01_24(a.v[1]), u2 = u01_24(a.v[2]), u3 = u01_24(a.v[3]);
+    float vx = near ? x + (u1 * 16.0f - 8.0f) : u1 * 130.0f - 65.0f;
+    const float vy = near ? y + (u2 * 16.0f - 8.0f) : u2 * 130.0f - 65.0f;
+    const float dd = sq(vx - x) + sq(vy - y);
+    vx = (dd < 36.0f) ? vx + 30.0f : vx;
+    const float s4 = ((u01_24(b.v[0]) + u01_24(b.v[1])) + u01_24(b.v[2])) + u01_24(b.v[3]);
+    const float base = quad == 0 ? 0.0f : (quad == 1 ? 90.0f : (quad == 2 ? 180.0f : -90.0f));
+    float vphi = base + 10.0f * ((s4 - 2.0f) * 1.73205077648162842f);
+    vphi = (vphi > 180.0f) ? vphi - 360.0f : vphi;
+    vphi = (vphi <= -180.0f) ? vphi + 360.0f : vphi;
+    return make_float4(vx, vy, 8.0f * u3, vphi);
+}
+
+// A warp owns 32 consecutive rows.  Phase 1, one lane per row: the rows to reset draw their ego state, read
+// the waypoint, project it (tracking columns) and write columns 0 .. veh_off - 1 -- a chain of dependent
+// global loads, so all rows of the warp take it at the same time.  Phase 2, the whole warp per reset row
+// (found with one ballot; ego position and episode number broadcast by shuffle): lane j (j, j + 32, ...)
+// generates vehicle slot j.  (With everything in one thread per row a launch was as slow as ~65 Philox
+// blocks in sequence for V = 32.)
+__global__ void __launch_bounds__(256)
+k_env_reset(const __grid_constant__ ResetParams R, int32_t *__restrict__ episode,
+            const int8_t *__restrict__ done, float *__restrict__ obs, int64_t ld,
+            int32_t *__restrict__ ref_idx, int8_t *__restrict__ virtual_red, int64_t B) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+    if (row0 >= B) return;
+    const int64_t i = row0 + lane;
+    const bool todo = i < B && (!done || done[i] != 0);
+    unsigned pending = __ballot_sync(0xffffffffu, todo);
+    if (!pending) return;
+    uint32_t ep = 0;
+    float x = 0.f, y = 0.f;
+    if (todo) {
+        ep = (uint32_t)episode[i];
+        episode[i] = (int32_t)(ep + 1u);
+        const Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)((uint64_t)i >> 32), ep, 0u, R.seed_lo, R.seed_hi);
+        const int p = R.fixed_path >= 0 ? R.fixed_path : (int)(((uint64_t)r.v[0] * (uint32_t)R.pv.n_paths) >> 32);
+        const int L = R.pv.L[p];
+        int idx = (int)(((uint64_t)r.v[1] * (uint32_t)R.span) >> 32) + 700;         // E2E:473-478
+        idx = idx < L ? idx : L - 1;                                                 // indexs2points clamp, DM:727-728
+        const float *tab = R.full[p];
+        x = tab[idx];
+        y = tab[L + idx];
+        const float phi = tab[2 * (size_t)L + idx];
+        const float v = CE2E_EXP_V * u01_24(r.v[2]);                                 // E2E:482
+        float *o = obs + i * ld;
+        o[0] = v; o[1] = 0.0f; o[2] = 0.0f; o[3] = x; o[4] = y; o[5] = phi;
         int k0, k1, bi;
         float best;
         const float2 *t_xy = R.pv.xy + (size_t)p * R.pv.stride;
@@ -1539,27 +1575,26 @@ __global__ void k_env_reset(const __grid_constant__ ResetParams R, int32_t *__re
         scan_min(t_xy, k0, k1, x, y, best, bi);
         tracking_from_index(t_xy, R.pv.phi + (size_t)p * R.pv.stride, L, R.pv.tail[p], R.task, bi, x, y, phi, v,
                             R.n_future, o + 6);
+        ref_idx[i] = p;
+        if (virtual_red) virtual_red[i] = (int8_t)(u01_24(r.v[3]) > 0.9f);             // E2E:120-124
     }
-    float *veh = o + 6 + 3 * (R.n_future + 1);
-    for (int j = 0; j < R.V; ++j) {
-        const Philox4 a = philox4x32_10(i_lo, i_hi, ep, 1u + 2u * (uint32_t)j, R.seed_lo, R.seed_hi);
-        const Philox4 b = philox4x32_10(i_lo, i_hi, ep, 2u + 2u * (uint32_t)j, R.seed_lo, R.seed_hi);
-        const bool near = (a.v[0] & 0xffffu) < 6554u;
-        const int quad = (int)((a.v[0] >> 16) & 3u);
-        const float u1 = u01_24(a.v[1]), u2 = u01_24(a.v[2]), u3 = u01_24(a.v[3]);
-        float vx = near ? x + (u1 * 16.0f - 8.0f) : u1 * 130.0f - 65.0f;
-        const float vy = near ? y + (u2 * 16.0f - 8.0f) : u2 * 130.0f - 65.0f;
-        const float dd = sq(vx - x) + sq(vy - y);
-        vx = (dd < 36.0f) ? vx + 30.0f : vx;
-        const float s4 = ((u01_24(b.v[0]) + u01_24(b.v[1])) + u01_24(b.v[2])) + u01_24(b.v[3]);
-        const float base = quad == 0 ? 0.0f : (quad == 1 ? 90.0f : (quad == 2 ? 180.0f : -90.0f));
-        float vphi = base + 10.0f * ((s4 - 2.0f) * 1.73205077648162842f);
-        vphi = (vphi > 180.0f) ? vphi - 360.0f : vphi;
-        vphi = (vphi <= -180.0f) ? vphi + 360.0f : vphi;
-        veh[4 * j] = vx; veh[4 * j + 1] = vy; veh[4 * j + 2] = CE2E_EXP_V * u3; veh[4 * j + 3] = vphi;
+    const int veh_off = 6 + 3 * (R.n_future + 1);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const int64_t ri = row0 + src;
+        const uint32_t rep = __shfl_sync(0xffffffffu, ep, src);
+        const float rx = __shfl_sync(0xffffffffu, x, src), ry = __shfl_sync(0xffffffffu, y, src);
+        float *veh = obs + ri * ld + veh_off;
+        for (int j = lane; j < R.V; j += 32) {
+            const float4 w = reset_vehicle((uint32_t)ri, (uint32_t)((uint64_t)ri >> 32), rep, j, R.seed_lo, R.seed_hi, rx, ry);
+            if ((reinterpret_cast<uintptr_t>(veh) & 15u) == 0) {
+                reinterpret_cast<float4 *>(veh)[j] = w;
+            } else {
+                veh[4 * j] = w.x; veh[4 * j + 1] = w.y; veh[4 * j + 2] = w.z; veh[4 * j + 3] = w.w;
+            }
+        }
     }
-    ref_idx[i] = p;
-    if (virtual_red) virtual_red[i] = (int8_t)(u01_24(r.v[3]) > 0.9f);             // E2E:120-124
 }
 
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -1627,7 +1662,7 @@ int model_step_common(const ce2e_paths *paths, int task, int path_index, const i
         for (int j = 0; j < V_out; ++j) {
             const int tc = turn ? turn->tc[j] : 0;
             P.turn_rs[j] = tc > 0 ? CE2E_R_LEFT : (tc < 0 ? -CE2E_R_RIGHT : 1.0f);
-            P.turn_rr[j] = tc > 0 ? 1.0f / CE2E_R_LEFT : (tc < 0 ? -(1.0f / CE2E_R_RIGHT) : 0.0f);
+            P.turn_rr[j] = tc > 0 ? host_consts().inv_r_left : (tc < 0 ? -host_consts().inv_r_right : 0.0f);
             P.turn_half[j] = tc != 0 ? CE2E_HALF : -1.0f;
         }
     } else {
@@ -1664,6 +1699,46 @@ int ce2e_set_tma(int mode) {
     const int old = g_use_tma;
     g_use_tma = mode < 0 ? 0 : (mode > 3 ? 1 : mode);
     return old;
+}
+int ce2e_config_set(const ce2e_config *cfg) {
+    static const ce2e_config defaults = {4.8, 2.0, 3.75, 3, 50.0, 8.0, 0.05, 0.8, 30.0, 0.02, 5.0, 0.05};
+    const ce2e_config c = cfg ? *cfg : defaults;
+    if (!(c.L > c.W && c.W > 0 && c.lane_width > 0 && c.lane_number >= 1 && c.crossroad_size > 0))
+        return fail(CE2E_ERR_SHAPE, "bad geometry in ce2e_config");
+    Ce2eConsts k;
+    // the reference's Python doubles, rounded to fp32 where TF would (when they meet a tensor)
+    k.lws = (float)((c.L - c.W) / 2);
+    k.half = (float)(c.crossroad_size / 2);
+    k.lw = (float)c.lane_width;
+    k.lw2 = (float)(2 * c.lane_width);
+    k.lw3 = (float)(c.lane_width * c.lane_number);
+    k.exp_v = (float)c.expected_v;
+    k.r_left = (float)(c.crossroad_size / 2 + 0.5 * c.lane_width);
+    k.r_right = (float)(c.crossroad_size / 2 - 2.5 * c.lane_width);
+    if (!(k.r_right > 0)) return fail(CE2E_ERR_SHAPE, "crossroad_size / 2 - 2.5 lane_width must be positive");
+    k.inv_r_left = 1.0f / k.r_left;
+    k.inv_r_right = 1.0f / k.r_right;
+    k.w_v = (float)c.w_devi_v; k.w_y = (float)c.w_devi_y; k.w_phi = (float)c.w_devi_phi;
+    k.w_yaw = (float)c.w_punish_yaw_rate; k.w_steer = (float)c.w_punish_steer; k.w_ax = (float)c.w_punish_a_x;
+    int n_dev = 0, cur = 0;
+    if (cudaGetDeviceCount(&n_dev) == cudaSuccess && n_dev > 0) {      // every device's constant bank
+        CE2E_CUDA(cudaGetDevice(&cur));
+        for (int d = 0; d < n_dev; ++d) {
+            CE2E_CUDA(cudaSetDevice(d));
+            CE2E_CUDA(cudaMemcpyToSymbol(c_consts, &k, sizeof(k)));
+        }
+        CE2E_CUDA(cudaSetDevice(cur));
+    } else {
+        cudaGetLastError();
+    }
+    host_consts() = k;
+    g_config = c;
+    return CE2E_OK;
+}
+int ce2e_config_get(ce2e_config *out) {
+    if (!out) return fail(CE2E_ERR_NULL, "NULL argument");
+    *out = g_config;
+    return CE2E_OK;
 }
 int ce2e_last_step_kernel(void) { return g_last_step_kernel; }
 const char *ce2e_last_error(void) { return g_err; }
@@ -1898,7 +1973,7 @@ int ce2e_env_reset(const ce2e_paths *paths, uint64_t seed, int32_t *episode, con
     R.task = paths->task; R.fixed_path = fixed_path < 0 ? -1 : fixed_path; R.V = V; R.n_future = n_future;
     R.span = paths->task == 0 ? 900 + 500 : (paths->task == 1 ? 1200 + 500 : 420 + 500);    // E2E:473-478
     R.seed_lo = (uint32_t)seed; R.seed_hi = (uint32_t)(seed >> 32);
-    k_env_reset<<<blocks_for(B, 128), 128, 0, (cudaStream_t)stream>>>(R, episode, done, obs, ld, ref_idx, virtual_red, B);
+    k_env_reset<<<blocks_for((B + 31) / 32, 8), 256, 0, (cudaStream_t)stream>>>(R, episode, done, obs, ld, ref_idx, virtual_red, B);
     return after_launch("k_env_reset");
 }
 

@@ -10,6 +10,7 @@ There is no CPU path: without a CUDA device or without the built library every c
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -42,6 +43,26 @@ def _wrap(t):
 _CUDA_CHECKED = False
 _RAW_STREAM = getattr(torch._C, '_cuda_getCurrentRawStream', None)
 
+# NVTX ranges named after the reference's tf.name_scope labels ('model_step' DM:119, 'compute_reward'
+# DM:188) around the corresponding launches, for nsys / ncu --nvtx timelines.  Off unless CE2E_NVTX=1.
+_NVTX = os.environ.get('CE2E_NVTX') == '1'
+
+
+class _nvtx_range(object):
+    __slots__ = ('name',)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
 
 def _device():
     global _CUDA_CHECKED
@@ -61,7 +82,9 @@ def to_device(x, dtype=torch.float32):
     """NumPy / list / torch (any device) -> CUDA tensor of `dtype` (no copy if already there)."""
     if isinstance(x, torch.Tensor):
         t = _raw(x)
-        if t.is_cuda and t.dtype == dtype:
+        # the launch stream and the path-table handle belong to the CURRENT device: a tensor living on
+        # another GPU is moved there (a silent peer access or an illegal address otherwise)
+        if t.is_cuda and t.dtype == dtype and t.device.index == torch.cuda.current_device():
             return t
         return t.to(device=_device(), dtype=dtype)
     return torch.as_tensor(np.asarray(x), device=_device()).to(dtype)
@@ -115,15 +138,11 @@ class VehicleDynamics(object):
     """DM:26-87."""
 
     def __init__(self, ):
-        self.vehicle_params = dict(C_f=-155495.0,  # front wheel cornering stiffness [N/rad]
-                                   C_r=-155495.0,  # rear wheel cornering stiffness [N/rad]
-                                   a=1.19,  # distance from CG to front axle [m]
-                                   b=1.46,  # distance from CG to rear axle [m]
-                                   mass=1520.,  # mass [kg]
-                                   I_z=2642.,  # polar moment of inertia at CG [kg*m^2]
-                                   miu=0.8,  # tire-road friction coefficient
-                                   g=9.81,  # acceleration of gravity [m/s^2]
-                                   )
+        # single-track model parameters, values of DM:37-44 (SI units): tyre cornering stiffness front /
+        # rear (N/rad), axle distances from the centre of gravity (m), mass (kg), yaw inertia (kg m^2),
+        # tyre-road friction, gravity (m/s^2)
+        self.vehicle_params = dict(C_f=-155495.0, C_r=-155495.0, a=1.19, b=1.46, mass=1520., I_z=2642.,
+                                   miu=0.8, g=9.81)
         a, b, mass, g = (self.vehicle_params[k] for k in ('a', 'b', 'mass', 'g'))
         self.vehicle_params.update(dict(F_zf=b * mass * g / (a + b), F_zr=a * mass * g / (a + b)))
 
@@ -171,6 +190,9 @@ def build_path_tables(task):
     direction to its successor in degrees.  Returns (path_list, path_len_list, control_points)."""
     if task not in TASKS:
         raise AssertionError('task must be one of %s' % (TASKS,))
+    from .endtoend_env_utils import get_config
+    cfg = get_config()                       # the reference reads module constants (EU:14-18)
+    CROSSROAD_SIZE, LANE_WIDTH, LANE_NUMBER = cfg.CROSSROAD_SIZE, cfg.LANE_WIDTH, cfg.LANE_NUMBER
     half = CROSSROAD_SIZE / 2
     line_m, per_m = 40, 30
     n_line = line_m * per_m
@@ -393,7 +415,7 @@ class EnvironmentModel(object):  # all tensors
     def _num_veh(self, obses):
         return (obses.shape[1] - self._veh_off) // self.per_veh_info_dim
 
-    def reset(self, obses, ref_indexes=None):  # input are all tensors
+    def reset(self, obses, ref_indexes=None):
         self.obses = obses
         self.ref_indexes = ref_indexes
         self.actions = None
@@ -414,7 +436,7 @@ class EnvironmentModel(object):  # all tensors
         return 0, ref
 
     # -- the hot call -----------------------------------------------------------------------
-    def rollout_out(self, actions):  # obses and actions are tensors, think of actions are in range [-1, 1]
+    def rollout_out(self, actions):
         """DM:118-126: one fused launch (ce2e_rollout_step)."""
         obs = self._obs
         B, D = obs.shape
@@ -437,9 +459,10 @@ class EnvironmentModel(object):  # all tensors
         nxt = padded_rows(B, veh_off + 4 * V_out, veh_off, dev)
         out5 = torch.empty((5, B), dtype=torch.float32, device=dev)
         scaled = torch.empty((B, 2), dtype=torch.float32, device=dev)
-        rc = _lib.load().ce2e_rollout_step(self.ref_path.handle, path_index, _ptr(ref), obs.data_ptr(), _ld(obs),
-                                           act.data_ptr(), self._turn_ref, V_in, V_out, int(self.num_future_data),
-                                           nxt.data_ptr(), _ld(nxt), out5.data_ptr(), scaled.data_ptr(), B, _stream())
+        with _nvtx_range('model_step'):
+            rc = _lib.load().ce2e_rollout_step(self.ref_path.handle, path_index, _ptr(ref), obs.data_ptr(), _ld(obs),
+                                               act.data_ptr(), self._turn_ref, V_in, V_out, int(self.num_future_data),
+                                               nxt.data_ptr(), _ld(nxt), out5.data_ptr(), scaled.data_ptr(), B, _stream())
         if rc:
             _lib.check(rc)
         self.actions = _wrap(scaled)
@@ -466,7 +489,7 @@ class EnvironmentModel(object):  # all tensors
         out[:, 6:6 + trk.shape[1]] = _raw(trk)
         return _wrap(out), _wrap(ref)
 
-    def _action_transformation_for_end2end(self, actions):  # [-1, 1]
+    def _action_transformation_for_end2end(self, actions):
         act = _rows(to_device(actions), 'actions', 2).contiguous()
         out = torch.empty_like(act)
         _lib.check(_lib.load().ce2e_action_transform(_ptr(act), _ptr(out), act.shape[0], _stream()))
@@ -481,9 +504,10 @@ class EnvironmentModel(object):  # all tensors
             raise ValueError('actions have %d rows for %d observations' % (act.shape[0], B))
         out5 = torch.empty((5, B), dtype=torch.float32, device=obs.device)
         d16 = torch.empty((16, B), dtype=torch.float32, device=obs.device)
-        _lib.check(_lib.load().ce2e_compute_rewards(_lib.TASK_ID[self.task], _ptr(obs), _ld(obs), _ptr(act),
-                                                    self._num_veh(obs), int(self.num_future_data), _ptr(out5),
-                                                    _ptr(d16), B, _stream()))
+        with _nvtx_range('compute_reward'):
+            _lib.check(_lib.load().ce2e_compute_rewards(_lib.TASK_ID[self.task], _ptr(obs), _ld(obs), _ptr(act),
+                                                        self._num_veh(obs), int(self.num_future_data), _ptr(out5),
+                                                        _ptr(d16), B, _stream()))
         reward_dict = {k: _wrap(d16[i]) for i, k in enumerate(REWARD_DICT_KEYS)}
         return tuple(_wrap(out5[i]) for i in range(5)) + (reward_dict,)
 

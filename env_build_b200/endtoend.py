@@ -99,6 +99,7 @@ class CrossroadEnd2end(object):
         self.use_graph = bool(use_graph)                 # replay step() as a CUDA graph (batched, device reset)
         self._bufs = None                                # static state, allocated by reset()
         self._graphs = [None, None]
+        self._views, self._cur_obs = {}, None
         self.v_light = 0                     # the model traffic has no signal phases: always green
         self.done_type = 'not_done_yet'
         self.reward_info = None
@@ -174,12 +175,15 @@ class CrossroadEnd2end(object):
                           d16=torch.zeros((16, B), **f32) if self.reward_info_enabled else None,
                           scaled=torch.zeros((B, 2), **f32), act=torch.zeros((B, 2), **f32),
                           done=torch.zeros((B,), dtype=torch.int8, device=dev),
+                          done_flag=torch.zeros((B,), dtype=torch.bool, device=dev),
                           episode=torch.zeros((B,), dtype=torch.int32, device=dev),
                           ref=torch.zeros((B,), dtype=torch.int32, device=dev),
                           red=torch.zeros((B,), dtype=torch.int8, device=dev))
         for b in self._bufs['obs']:
             b.zero_()
         self._cur = 0
+        self._views = {}
+        self.action_buffer = self._bufs['act']       # a policy may write its [B, 2] actions here and pass it to step()
 
     def _device_reset(self, obs, done):
         """ce2e_env_reset on the rows of `obs` whose `done` code is non-zero (done None: all rows)."""
@@ -213,7 +217,7 @@ class CrossroadEnd2end(object):
             buf.copy_(to_device(obs))
             self.ref_indexes.copy_(to_device(ref, torch.int32))
             self._fill_tracking(buf, self.ref_indexes)
-        self.obs = _wrap(buf)
+        self.obs = self._cur_obs = _wrap(buf)
         self.action = None
         self.reward_info = None
         self.done_type = 'not_done_yet'
@@ -233,67 +237,90 @@ class CrossroadEnd2end(object):
                                              int(self.num_future_data), int(self.v_light), _ptr(nxt), nxt.stride(0),
                                              _ptr(b['out5']), _ptr(b['d16']), _ptr(b['scaled']), _ptr(b['done']),
                                              self.num_envs, _stream()))
+        if self.num_envs > 1:
+            torch.ne(b['done'], 0, out=b['done_flag'])
         if self.auto_reset and self.num_envs > 1 and self.traffic_init is None:
             self._device_reset(nxt, b['done'])
+
+    def _views_for(self, cur):
+        """The wrapped views a batched step returns when the observations are in buffer `cur` (cached: a
+        step must not cost tens of microseconds of Python)."""
+        v = self._views.get(cur)
+        if v is None:
+            b = self._bufs
+            info = dict(done_code=_wrap(b['done']), ref_index=b['ref'])
+            if b['d16'] is not None:
+                info['reward_info'] = {k: _wrap(b['d16'][i]) for i, k in enumerate(REWARD_DICT_KEYS)}
+            v = dict(obs=_wrap(b['obs'][cur]), scaled=_wrap(b['scaled']), info=info,
+                     ret=(_wrap(b['obs'][cur]), _wrap(b['out5'][0]), _wrap(b['done_flag']), info))
+            v['ret'] = (v['obs'],) + v['ret'][1:]
+            self._views[cur] = v
+        return v
+
+    def _capture(self, cur):
+        b = self._bufs
+        self.ref_path.handle                   # create the device tables outside the capture
+        state = (b['obs'][0], b['obs'][1], b['episode'], b['ref'])
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            snap = [t.clone() for t in state]
+            self._enqueue_step(cur)            # warm-up outside the capture, then undo its effects
+            for t, c in zip(state, snap):
+                t.copy_(c)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue_step(cur)
+        self._graphs[cur] = g
 
     def step(self, action):
         """E2E:132-144.  Batched environments return views of static device buffers (observations,
         rewards, done flags, info tensors): they are overwritten by the next step() -- clone what must
         be kept.  With auto_reset the returned observation rows of finished environments are already
-        those of their next episode, and `done` still flags them."""
+        those of their next episode, and `done` still flags them.  `action` may be `env.action_buffer`
+        itself (filled in place by the policy), which saves the copy."""
         B = self.num_envs
         if self._bufs is None:
             raise RuntimeError('call reset() before step()')
         b = self._bufs
-        act = to_device(np.asarray(action, np.float32) if not isinstance(action, torch.Tensor) else action)
-        b['act'].copy_(act.reshape(B, 2), non_blocking=True)
+        if action is not b['act']:
+            act = action if isinstance(action, torch.Tensor) else to_device(np.asarray(action, np.float32))
+            b['act'].copy_(act.reshape(B, 2), non_blocking=True)
         cur = self._cur
         # a caller may have assigned env.obs / env.ref_indexes (the reference's attributes): adopt them
-        if self.obs is not None and self.obs.data_ptr() != b['obs'][cur].data_ptr():
-            b['obs'][cur].copy_(to_device(self.obs).reshape(B, self.obs_dim), non_blocking=True)
-        if self.ref_indexes is not None and self.ref_indexes.data_ptr() != b['ref'].data_ptr():
-            b['ref'].copy_(to_device(self.ref_indexes, torch.int32).reshape(B), non_blocking=True)
+        if self.obs is not self._cur_obs:
+            if self.obs is not None and self.obs.data_ptr() != b['obs'][cur].data_ptr():
+                b['obs'][cur].copy_(to_device(self.obs).reshape(B, self.obs_dim), non_blocking=True)
+        if self.ref_indexes is not b['ref']:
+            if self.ref_indexes is not None and self.ref_indexes.data_ptr() != b['ref'].data_ptr():
+                b['ref'].copy_(to_device(self.ref_indexes, torch.int32).reshape(B), non_blocking=True)
             self.ref_indexes = b['ref']
         if self.use_graph and B > 1 and self.traffic_init is None:
             if self._graphs[cur] is None:
-                self.ref_path.handle
-                s = torch.cuda.Stream()
-                s.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s):
-                    snap = [t.clone() for t in (b['obs'][0], b['obs'][1], b['episode'], b['ref'])]
-                    self._enqueue_step(cur)            # warm-up outside the capture, then undo its effects
-                    for t, c in zip((b['obs'][0], b['obs'][1], b['episode'], b['ref']), snap):
-                        t.copy_(c)
-                torch.cuda.current_stream().wait_stream(s)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._enqueue_step(cur)
-                self._graphs[cur] = g
-                for t, c in zip((b['obs'][0], b['obs'][1], b['episode'], b['ref']), snap):
-                    t.copy_(c)                         # (capture does not execute, but keep the state exact)
+                self._capture(cur)
             self._graphs[cur].replay()
         else:
             self._enqueue_step(cur)
-        self._cur = 1 - cur
+        self._cur = cur = 1 - cur
+        if B > 1:
+            v = self._views_for(cur)
+            self.action, self.obs, self._cur_obs, self.done_code = v['scaled'], v['obs'], v['obs'], v['info']['done_code']
+            if self.auto_reset and self.traffic_init is not None:
+                self._reset_done_rows(b['done'])
+            return v['ret']
         self.action = _wrap(b['scaled'])
-        self.obs = _wrap(b['obs'][self._cur])
+        self.obs = self._cur_obs = _wrap(b['obs'][cur])
         self.done_code = _wrap(b['done'])
-        reward, done, d16 = b['out5'][0], b['done'], b['d16']
-        if B == 1:
-            code = int(done.item())
-            self.done_type = DONE_TYPES[code]
-            if d16 is not None:
-                self.reward_info = {k: float(d16[i, 0]) for i, k in enumerate(REWARD_DICT_KEYS)}
-                self.reward_info.update({'final_rew': float(reward[0])})
-            info = dict(reward_info=self.reward_info, ref_index=int(self.ref_indexes[0]), done_type=self.done_type,
-                        ego_dynamics=self._ego_dynamics_dict())
-            return self.obs.numpy()[0], float(reward[0]), int(code != 0), info
-        info = dict(done_code=self.done_code, ref_index=self.ref_indexes)
+        reward, d16 = b['out5'][0], b['d16']
+        code = int(b['done'].item())
+        self.done_type = DONE_TYPES[code]
         if d16 is not None:
-            info['reward_info'] = {k: _wrap(d16[i]) for i, k in enumerate(REWARD_DICT_KEYS)}
-        if self.auto_reset and self.traffic_init is not None:
-            self._reset_done_rows(done)
-        return self.obs, _wrap(reward), _wrap(done != 0), info
+            self.reward_info = {k: float(d16[i, 0]) for i, k in enumerate(REWARD_DICT_KEYS)}
+            self.reward_info.update({'final_rew': float(reward[0])})
+        info = dict(reward_info=self.reward_info, ref_index=int(self.ref_indexes[0]), done_type=self.done_type,
+                    ego_dynamics=self._ego_dynamics_dict())
+        return self.obs.numpy()[0], float(reward[0]), int(code != 0), info
 
     def _reset_done_rows(self, done):
         """Host-side auto-reset, only for a user-supplied `traffic_init` (synchronises)."""
@@ -360,7 +387,7 @@ class CrossroadEnd2end(object):
         o = self.obs.numpy()[0]
         return dict(v_x=o[0], v_y=o[1], r=o[2], x=o[3], y=o[4], phi=o[5], l=self.ego_l, w=self.ego_w)
 
-    def _action_transformation_for_end2end(self, action):  # [-1, 1]
+    def _action_transformation_for_end2end(self, action):
         a = self.env_model._action_transformation_for_end2end(np.asarray(action, np.float32).reshape(-1, 2))
         return a.numpy()[0] if np.ndim(action) == 1 else a
 

@@ -4,6 +4,7 @@ Mirror of the parts of the reference's endtoend_env_utils.py the model hot path 
 (reference endtoend_env_utils.py:14-46, :73-104, :232-237); the SUMO coordinate glue of
 that module is out of scope.
 """
+import dataclasses
 from collections import OrderedDict
 
 L, W = 4.8, 2.0
@@ -11,6 +12,48 @@ LANE_WIDTH = 3.75
 LANE_NUMBER = 3
 CROSSROAD_SIZE = 50
 EXPECTED_V = 8.
+
+
+@dataclasses.dataclass(frozen=True)
+class CrossroadConfig(object):
+    """What the reference bakes in as module constants and literals, as one frozen record: geometry
+    (reference endtoend_env_utils.py:14-18), EXPECTED_V, and the reward weights of compute_rewards
+    (reference dynamics_and_models.py:297-298).  Defaults are the reference's values.  `set_config`
+    pushes a record into the kernels' constant block (ce2e_config_set) and makes it the one new
+    ReferencePath tables are built from; existing ReferencePath objects keep their tables."""
+    L: float = L
+    W: float = W
+    LANE_WIDTH: float = LANE_WIDTH
+    LANE_NUMBER: int = LANE_NUMBER
+    CROSSROAD_SIZE: float = CROSSROAD_SIZE
+    EXPECTED_V: float = EXPECTED_V
+    w_devi_v: float = 0.05
+    w_devi_y: float = 0.8
+    w_devi_phi: float = 30.
+    w_punish_yaw_rate: float = 0.02
+    w_punish_steer: float = 5.
+    w_punish_a_x: float = 0.05
+
+
+_ACTIVE = CrossroadConfig()
+
+
+def get_config():
+    return _ACTIVE
+
+
+def set_config(cfg=None):
+    """Activate `cfg` (None: the reference's defaults) for all later kernel launches and path tables.
+    Returns the previous record.  Process wide; do not call while kernels are in flight."""
+    global _ACTIVE
+    from . import _lib
+    cfg = CrossroadConfig() if cfg is None else cfg
+    c = _lib.Config(cfg.L, cfg.W, cfg.LANE_WIDTH, int(cfg.LANE_NUMBER), cfg.CROSSROAD_SIZE, cfg.EXPECTED_V, cfg.w_devi_v,
+                    cfg.w_devi_y, cfg.w_devi_phi, cfg.w_punish_yaw_rate, cfg.w_punish_steer, cfg.w_punish_a_x)
+    import ctypes
+    _lib.check(_lib.load().ce2e_config_set(ctypes.byref(c)))
+    old, _ACTIVE = _ACTIVE, cfg
+    return old
 
 # how many vehicles of each route class an observation holds, per ego task (EU:21-23)
 VEHICLE_MODE_DICT = dict(left=OrderedDict(dl=2, du=2, ud=2, ul=2),

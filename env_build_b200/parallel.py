@@ -5,6 +5,16 @@ find_closest_point, runs over waypoints, not rows), so the path shards by contig
 blocks with NO data-path collective.  torch.distributed (NCCL over NVLink on GPUs, gloo in
 the CPU tests) is used only to scatter a batch that lives on one rank and to gather the
 per-row returns; path tables and configuration are replicated at construction.
+
+Two ways to feed a `ShardedRollout`:
+
+* `scatter(obses, ref_indexes, tape)`: any row count, inputs in the API layout ([B, D], [B],
+  [H, B, 2]).  Ragged shards are padded to the longest one for the collective.
+* `stage(...)` once on the source rank, then `scatter_staged(...)` per rollout: the source keeps the
+  batch in the layout the ranks' static buffers have (padded observation rows, action tape blocked
+  by rank), so the collectives send VIEWS of it straight into those buffers: no pad, no copy, no
+  permute on either side.  Needs B % world_size == 0.  With `slots=2` the next rollout's inputs can
+  travel (on a side stream) while the current one computes.
 """
 import torch
 import torch.distributed as dist
@@ -29,22 +39,30 @@ def _group_info(group=None):
 
 def scatter_rows(full, B, tail_shape, dtype, device, src=0, group=None):
     """Rank `src` holds `full` [B, *tail_shape]; every rank returns its row block.
-    Ragged shards are padded to the longest one for the collective and trimmed after."""
+    Equal shards are sent as views of `full`; ragged shards are padded to the longest one for the
+    collective and trimmed after."""
     W, rank = _group_info(group)
     lo, hi = shard_bounds(B, W, rank)
     if W == 1:
         return full[lo:hi].to(device=device, dtype=dtype)
-    longest = max(shard_sizes(B, W))
+    sizes = shard_sizes(B, W)
+    longest = max(sizes)
     recv = torch.empty((longest,) + tuple(tail_shape), dtype=dtype, device=device)
     chunks = None
     if rank == src:
-        full = full.to(device=device, dtype=dtype)
-        chunks = []
-        for r in range(W):
-            a, b = shard_bounds(B, W, r)
-            c = torch.zeros((longest,) + tuple(tail_shape), dtype=dtype, device=device)
-            c[:b - a] = full[a:b]
-            chunks.append(c)
+        full = full.to(device=device, dtype=dtype).contiguous()
+        if min(sizes) == longest:
+            chunks = list(full.split(longest, 0))
+        else:
+            chunks = []
+            for r in range(W):
+                a, b = shard_bounds(B, W, r)
+                if b - a == longest:
+                    chunks.append(full[a:b])
+                else:
+                    c = torch.zeros((longest,) + tuple(tail_shape), dtype=dtype, device=device)
+                    c[:b - a] = full[a:b]
+                    chunks.append(c)
     dist.scatter(recv, chunks, src=src, group=group)
     return recv[:hi - lo]
 
@@ -55,42 +73,104 @@ def gather_rows(local, B, dst=0, group=None):
     W, rank = _group_info(group)
     if W == 1:
         return local
-    longest = max(shard_sizes(B, W))
-    pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[:local.shape[0]] = local
-    bufs = [torch.empty_like(pad) for _ in range(W)] if rank == dst else None
-    dist.gather(pad, bufs, dst=dst, group=group)
+    sizes = shard_sizes(B, W)
+    longest = max(sizes)
+    if local.shape[0] != longest:
+        pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+        local = pad
+    out = torch.empty((W, longest) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) \
+        if rank == dst else None
+    dist.gather(local.contiguous(), list(out.unbind(0)) if rank == dst else None, dst=dst, group=group)
     if rank != dst:
         return None
-    return torch.cat([bufs[r][:n] for r, n in enumerate(shard_sizes(B, W))], 0)
+    if min(sizes) == longest:
+        return out.reshape((B,) + tuple(local.shape[1:]))
+    return torch.cat([out[r, :n] for r, n in enumerate(sizes)], 0)
+
+
+class StagedBatch(object):
+    """A global batch on the source rank in scatter-ready layout (see ShardedRollout.stage)."""
+
+    def __init__(self, obs_store, ref, tape, b, ld):
+        self.obs_store, self.ref, self.tape, self.b, self.ld = obs_store, ref, tape, b, ld
 
 
 class ShardedRollout(object):
     """Data-parallel H-step rollout: rank `src` supplies [B, D] observations, [B] path indexes and
     an [H, B, 2] action tape; every rank rolls out its row block with `make_runner(b_local)`
     (a RolloutGraph-like object with load/run/out5) and rank `src` receives the per-row
-    returns sum_t out5[t] as [B, 5]."""
+    returns sum_t out5[t] as [B, 5].  `slots` runners per rank allow one rollout's exchange to overlap
+    another's compute."""
 
-    def __init__(self, make_runner, B, D, H, device, group=None):
+    def __init__(self, make_runner, B, D, H, device, group=None, slots=1):
         self.B, self.D, self.H, self.device, self.group = int(B), int(D), int(H), device, group
         W, rank = _group_info(group)
+        self.world, self.rank = W, rank
         lo, hi = shard_bounds(B, W, rank)
         self.lo, self.hi = lo, hi
-        self.runner = make_runner(hi - lo)
+        self.runners = [make_runner(hi - lo) for _ in range(int(slots))]
+        self.runner = self.runners[0]
+        self._gather_out = {}
 
-    def scatter(self, obses=None, ref_indexes=None, tape=None, src=0):
+    # -- generic path -------------------------------------------------------------------------
+    def scatter(self, obses=None, ref_indexes=None, tape=None, src=0, slot=0, has_ref=True, has_tape=True):
+        """`has_ref` / `has_tape` must agree on every rank (mode != 'training' needs no path indexes; a
+        closed-loop runner needs no tape): the matching collective is skipped when False."""
         B = self.B
         obs = scatter_rows(obses, B, (self.D,), torch.float32, self.device, src, self.group)
-        ref = scatter_rows(ref_indexes, B, (), torch.int32, self.device, src, self.group)
-        tp = tape
-        if tape is not None and _group_info(self.group)[1] == src:
-            tp = tape.permute(1, 0, 2)                    # rows first for the row scatter
-        tp = scatter_rows(tp, B, (self.H, 2), torch.float32, self.device, src, self.group)
-        self.runner.load(obs, ref, tp.permute(1, 0, 2))
+        ref = scatter_rows(ref_indexes, B, (), torch.int32, self.device, src, self.group) if has_ref else None
+        tp = None
+        if has_tape:
+            tp = tape
+            if tape is not None and self.rank == src:
+                tp = tape.permute(1, 0, 2)                # rows first for the row scatter
+            tp = scatter_rows(tp, B, (self.H, 2), torch.float32, self.device, src, self.group).permute(1, 0, 2)
+        self.runners[slot].load(obs, ref, tp)
 
-    def run(self):
-        self.runner.run()
+    # -- staged path: views straight into the runners' static buffers -----------------------------
+    def stage(self, obses, ref_indexes, tape):
+        """On the source rank: the global batch as (padded observation rows [B, ld] in one allocation,
+        [B] int32 path indexes, action tape [W, H, b, 2] blocked by rank).  One-time layout work, outside
+        the per-rollout exchange."""
+        import numpy as np
+        from .dynamics_and_models import padded_rows
 
-    def gather_returns(self, dst=0):
-        ret = self.runner.out5.sum(0).t().contiguous()    # [b_local, 5]
+        def to_device(x, dtype=torch.float32):
+            t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
+            return t.to(device=self.device, dtype=dtype)
+        B, W = self.B, self.world
+        if B % W:
+            raise ValueError('the staged scatter needs B %% world_size == 0 (B=%d, W=%d)' % (B, W))
+        b = B // W
+        r = self.runner
+        ld, off = r.obs0.stride(0), r.obs0.storage_offset()
+        g = padded_rows(B, self.D, r.model._veh_off, self.device)
+        assert g.stride(0) == ld and g.storage_offset() == off
+        g.copy_(to_device(obses))
+        ref = to_device(ref_indexes, torch.int32).reshape(B).contiguous()
+        tp = to_device(tape).reshape(self.H, W, b, 2).permute(1, 0, 2, 3).contiguous()
+        return StagedBatch(g._base, ref, tp, b, ld)
+
+    def scatter_staged(self, staged=None, slot=0, src=0):
+        """Three collectives whose send buffers are views of the staged batch and whose receive buffers
+        are the runner's own static buffers (RolloutGraph.obs0 / .ref / .tape)."""
+        r = self.runners[slot]
+        b, ld = r.B, r.obs0.stride(0)
+        store = r.obs0._base[:b * ld]
+        if self.world == 1:
+            store.copy_(staged.obs_store[:b * ld])
+            r.ref.copy_(staged.ref)
+            r.tape.copy_(staged.tape[0])
+            return
+        root = self.rank == src
+        dist.scatter(store, list(staged.obs_store[:self.B * ld].split(b * ld)) if root else None, src=src, group=self.group)
+        dist.scatter(r.tape, list(staged.tape.unbind(0)) if root else None, src=src, group=self.group)
+        dist.scatter(r.ref, list(staged.ref.split(b)) if root else None, src=src, group=self.group)
+
+    def run(self, slot=0):
+        self.runners[slot].run()
+
+    def gather_returns(self, dst=0, slot=0):
+        ret = self.runners[slot].out5.sum(0).t().contiguous()    # [b_local, 5]
         return gather_rows(ret, self.B, dst, self.group)

@@ -50,6 +50,7 @@ class RolloutGraph(object):
         self.ref = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.final_obs = _wrap(self.buf[(H - 1) % 2])
         self._graph = None
+        self._graph_key, self._graph_path, self._filled_index = None, None, None
         self.use_graph = use_graph
         self.launches_per_run = 0
 
@@ -57,15 +58,16 @@ class RolloutGraph(object):
         self.obs0.copy_(to_device(obses), non_blocking=True)
         if ref_indexes is not None:
             self.ref.copy_(to_device(ref_indexes, torch.int32).reshape(-1), non_blocking=True)
+            self._filled_index = None
         if tape is not None:
             self.tape.copy_(to_device(tape), non_blocking=True)
 
     def _enqueue(self):
         m, lib = self.model, _lib.load()
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        training = m.mode == 'training'
-        path_index = 0 if training else int(m.ref_path.ref_index)
-        ref = _ptr(self.ref) if training else None
+        # the path index always travels through the device-side `ref` buffer (filled by run() when the model
+        # is not in 'training' mode), so a captured graph follows later add_traj / set_path calls
+        path_index, ref = 0, _ptr(self.ref)
         handle = m.ref_path.handle
         src = self.obs0
         ld = self.obs0.stride(0)
@@ -86,6 +88,17 @@ class RolloutGraph(object):
             src = dst
 
     def run(self):
+        m = self.model
+        if m.mode != 'training':
+            idx = int(m.ref_path.ref_index)
+            if idx != self._filled_index:
+                self.ref.fill_(idx)
+                self._filled_index = idx
+        # a captured graph holds the table handle of the ReferencePath it was captured with
+        key = (id(m.ref_path), m.ref_path.handle.value if hasattr(m.ref_path.handle, 'value') else int(m.ref_path.handle))
+        if self._graph is not None and key != self._graph_key:
+            self._graph = None
+        self._graph_key, self._graph_path = key, m.ref_path
         if not self.use_graph:
             self._enqueue()
             self.launches_per_run = 1 if self.fused else self.H

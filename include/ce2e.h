@@ -60,6 +60,22 @@ typedef struct ce2e_paths ce2e_paths;
 int ce2e_version(void);
 const char *ce2e_last_error(void);
 
+/* Scenario constants the reference bakes in at import: geometry (EU:14-18: L, W, LANE_WIDTH, LANE_NUMBER,
+ * CROSSROAD_SIZE; EXPECTED_V) and the reward weights of compute_rewards (DM:297-298).  Defaults are the
+ * reference's values.  ce2e_config_set(NULL) restores them; the setting is process wide, applies to every
+ * device and to every later launch (launch nothing concurrently).  Reference-path tables are inputs
+ * (ce2e_paths_create), so a caller that changes the geometry also passes matching tables.         */
+typedef struct ce2e_config {
+    double L, W;                 /* ego / vehicle length and width: circle centres at +-(L - W)/2, DM:209 */
+    double lane_width;           /* LANE_WIDTH */
+    int lane_number;             /* LANE_NUMBER */
+    double crossroad_size;       /* CROSSROAD_SIZE */
+    double expected_v;           /* EXPECTED_V (delta_v of the tracking error, DM:760) */
+    double w_devi_v, w_devi_y, w_devi_phi, w_punish_yaw_rate, w_punish_steer, w_punish_a_x;   /* DM:297-298 */
+} ce2e_config;
+int ce2e_config_set(const ce2e_config *cfg);
+int ce2e_config_get(ce2e_config *out);
+
 /* Process-wide option, default 0.  enable != 0: ce2e_rollout_step takes sin / cos of the SURROUNDING
  * VEHICLES' headings (DM:220-224, DM:409-410) from the special-function unit (abs. error <= 2^-21.4
  * instead of <= 1.5 ulp).  Results stay inside the 1e-5 parity tolerance; everything else is

@@ -143,3 +143,36 @@ def test_backward_tiled_equals_scalar(dm, V):
     for a, b in zip(got[0], got[1]):
         assert np.isfinite(a).all() and np.isfinite(b).all()
         assert np.allclose(a, b, rtol=1e-4, atol=1e-4), float(np.abs(a - b).max())
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_backward_against_reference_gradient_golden(dm, task):
+    """ce2e_rollout_step_backward against tests/golden/grad_<task>.npz: the vector-Jacobian product of the
+    UNMODIFIED reference rollout_out under the shim's GradientTape (TensorFlow's autodiff rules;
+    make_golden_grad.py).  allclose(rtol=1e-4, atol=1e-4); rows whose closest waypoint is a near-tie
+    (a different reference point in fp32) are excluded."""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, 'grad_%s.npz' % task), allow_pickle=False))
+    model = dm.EnvironmentModel(task, mode='training')
+    obs = torch.tensor(g['obs'], device='cuda', requires_grad=True)
+    act = torch.tensor(g['act'], device='cuda', requires_grad=True)
+    model.reset(obs, g['ref'])
+    res = model.rollout_out(act)
+    # the forward of the differentiable path equals the reference's forward
+    assert np.allclose(res[0].detach().cpu().numpy()[:, :6], g['next_obs'][:, :6], rtol=1e-5, atol=1e-5)
+    for a, b in zip(res[1:], g['out5']):
+        assert np.allclose(a.detach().cpu().numpy(), b, rtol=1e-5, atol=1e-5)
+    loss = (res[0][:, :9] * torch.tensor(g['g_next9'], device='cuda')).sum() + \
+        (torch.stack(res[1:]) * torch.tensor(g['g_out5'], device='cuda')).sum()
+    loss.backward()
+    om = orc.EnvironmentModel(task, mode='training', path_list=model.ref_path.path_list)
+    om.reset(g['obs'], g['ref'])
+    _, margin = om.compute_next_obses(g['obs'], orc.action_transformation(g['act']), return_margin=True)
+    ok = margin > 1e-3
+    assert ok.mean() > 0.95
+    go, ga = obs.grad.cpu().numpy(), act.grad.cpu().numpy()
+    assert np.allclose(go[ok][:, :9], g['grad_obs9'][ok], rtol=1e-4, atol=1e-4), \
+        float(np.abs(go[ok][:, :9] - g['grad_obs9'][ok]).max())
+    assert np.allclose(ga[ok], g['grad_act'][ok], rtol=1e-4, atol=1e-4), float(np.abs(ga[ok] - g['grad_act'][ok]).max())
+    assert np.abs(go[:, 9:]).max() == 0

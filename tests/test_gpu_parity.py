@@ -878,3 +878,54 @@ def test_tma_kernel_is_the_default_path(dm):
         assert _lib.load().ce2e_last_step_kernel() == 1       # 1 = k_model_step (cp.async)
     finally:
         _lib.set_tma(old)
+
+
+def test_config_set_changes_only_its_term(dm):
+    """CrossroadConfig / ce2e_config_set (the reference's baked-in constants as one frozen
+    record).  Doubling one reward weight (DM:297-298) doubles that scaled term of the reward dict and
+    changes nothing else; a narrower lane (EU:15) moves the road terms and leaves the vehicle terms alone;
+    set_config(None) restores the reference's values bit for bit."""
+    from env_build_b200 import synthetic as syn
+    from env_build_b200.endtoend_env_utils import CrossroadConfig, set_config, get_config
+    rng = np.random.default_rng(9)
+    task, B, V = 'straight', 2000, 9
+    model = dm.EnvironmentModel(task, mode='selecting')
+    obs = syn.make_obs(rng, B, task, V, model.ref_path.path_list, 1)
+    sc = orc.action_transformation(syn.make_actions(rng, 1, B)[0])
+
+    def rewards():
+        r = model.compute_rewards(obs, sc)
+        return [x.numpy() for x in r[:5]], {k: v.numpy() for k, v in r[5].items()}
+    base5, base_d = rewards()
+    assert get_config() == CrossroadConfig()
+    try:
+        set_config(CrossroadConfig(w_devi_y=1.6))
+        got5, got_d = rewards()
+        bits_equal(got_d['scaled_devi_y'], np.float32(2) * base_d['scaled_devi_y'])
+        for k in base_d:
+            if k != 'scaled_devi_y':
+                bits_equal(got_d[k], base_d[k])
+        for i in range(1, 5):
+            bits_equal(got5[i], base5[i])
+        assert not np.array_equal(got5[0], base5[0])
+        set_config(CrossroadConfig(LANE_WIDTH=3.5))
+        got5, got_d = rewards()
+        bits_equal(got_d['veh2veh4training'], base_d['veh2veh4training'])
+        bits_equal(got_d['veh2veh4real'], base_d['veh2veh4real'])
+        bits_equal(got5[0], base5[0])
+        assert not np.array_equal(got_d['veh2road4training'], base_d['veh2road4training'])
+    finally:
+        set_config(None)
+    got5, got_d = rewards()
+    for a, b in zip(got5, base5):
+        bits_equal(a, b)
+    # the fused step sees the same constant block
+    model.add_traj(obs, 1)
+    r0 = model.rollout_out(syn.make_actions(np.random.default_rng(1), 1, B)[0])[1].numpy()
+    try:
+        set_config(CrossroadConfig(w_punish_steer=10.))
+        model.add_traj(obs, 1)
+        r1 = model.rollout_out(syn.make_actions(np.random.default_rng(1), 1, B)[0])[1].numpy()
+    finally:
+        set_config(None)
+    assert not np.array_equal(r0, r1)

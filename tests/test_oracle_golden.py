@@ -253,3 +253,31 @@ def test_env_reset_rows_distribution():
     assert (r2 == ref[sub]).all()
     o3, _, _ = orc.env_reset_rows(1234, sub, np.ones(3, int), task, paths, 8)
     assert not np.array_equal(o3, o2)
+
+
+@pytest.mark.parametrize('task', TASKS)
+def test_gradient_golden_matches_torch_oracle(task):
+    """tests/golden/grad_<task>.npz (vector-Jacobian product of the UNMODIFIED reference rollout_out under
+    the shim's GradientTape, TensorFlow's autodiff rules) against torch.autograd on the float64 restatement
+    in oracle/torch_model.py: two independent derivations of the same gradient."""
+    import os
+    import torch
+    from conftest import GOLDEN
+    from oracle import torch_model as tm
+    g = dict(np.load(os.path.join(GOLDEN, 'grad_%s.npz' % task), allow_pickle=False))
+    paths = orc.construct_ref_paths(task)[0]
+    obs = torch.tensor(g['obs'], dtype=torch.float64, requires_grad=True)
+    act = torch.tensor(g['act'], dtype=torch.float64, requires_grad=True)
+    res = tm.rollout_out(obs, act, task, g['ref'], paths, orc.VEHICLE_MODE_LIST[task])
+    loss = (res[0][:, :9] * torch.tensor(g['g_next9'], dtype=torch.float64)).sum() + \
+        (torch.stack(res[1:]) * torch.tensor(g['g_out5'], dtype=torch.float64)).sum()
+    loss.backward()
+    om = orc.EnvironmentModel(task, mode='training', path_list=paths)
+    om.reset(g['obs'], g['ref'])
+    _, margin = om.compute_next_obses(g['obs'], orc.action_transformation(g['act']), return_margin=True)
+    ok = margin > 1e-3                    # same closest waypoint in fp32 and float64
+    assert ok.mean() > 0.95
+    # the golden's forward ran in fp32, the oracle's in float64: gradients agree to fp32 forward accuracy
+    assert np.allclose(obs.grad.numpy()[ok][:, :9], g['grad_obs9'][ok], rtol=2e-4, atol=2e-4)
+    assert np.allclose(act.grad.numpy()[ok], g['grad_act'][ok], rtol=2e-4, atol=2e-4)
+    assert np.abs(obs.grad.numpy()[:, 9:]).max() == 0

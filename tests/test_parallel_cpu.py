@@ -97,3 +97,71 @@ def test_sharded_rollout_gloo_world2(tmp_path, B):
     want = r.out5.sum(0).t().numpy()
     assert got.shape == (B, 5)
     assert np.array_equal(got.view(np.int32), want.view(np.int32))
+
+
+class StaticRunner(OracleRunner):
+    """OracleRunner with RolloutGraph's static buffers (obs0 padded rows, ref, tape), so that the
+    staged scatter can write straight into them."""
+
+    def __init__(self, b):
+        from env_build_b200.dynamics_and_models import padded_rows
+        OracleRunner.__init__(self, b)
+        self.B = b
+        self.model = type('M', (), dict(_veh_off=9))()
+        self.obs0 = padded_rows(b, 9 + 4 * V, 9, torch.device('cpu'))
+        self.ref = torch.zeros((b,), dtype=torch.int32)
+        self.tape = torch.zeros((H, b, 2), dtype=torch.float32)
+
+    def run(self):
+        self.load(self.obs0.clone(), self.ref, self.tape)
+        OracleRunner.run(self)
+
+
+def _worker_staged(rank, world, port, B, out_path):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        obs, ref, tape = _inputs(B)
+        sr = par.ShardedRollout(StaticRunner, B, obs.shape[1], H, torch.device('cpu'), slots=2)
+        staged = sr.stage(obs, ref, tape) if rank == 0 else None
+        for slot in (0, 1):
+            sr.scatter_staged(staged, slot=slot)
+            r = sr.runners[slot]
+            assert np.array_equal(r.obs0.numpy(), obs[sr.lo:sr.hi]) and np.array_equal(r.ref.numpy(), ref[sr.lo:sr.hi])
+            assert np.array_equal(r.tape.numpy(), tape[:, sr.lo:sr.hi])
+        sr.run(slot=1)
+        ret = sr.gather_returns(slot=1)
+        if rank == 0:
+            np.save(out_path, ret.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_staged_scatter_gloo_world2(tmp_path):
+    """The no-copy exchange: views of the source's staged batch land in the ranks' static buffers."""
+    B = 64
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / 'ret.npy')
+    mp.spawn(_worker_staged, args=(2, port, B, out), nprocs=2, join=True)
+    got = np.load(out)
+    obs, ref, tape = _inputs(B)
+    r = OracleRunner(B)
+    r.load(torch.from_numpy(obs), torch.from_numpy(ref), torch.from_numpy(tape))
+    r.run()
+    assert np.array_equal(got.view(np.int32), r.out5.sum(0).t().numpy().view(np.int32))
+
+
+def test_scatter_without_ref_or_tape():
+    """mode != 'training' has no per-row path indexes, a closed-loop runner no tape (world size 1 here)."""
+    class R(object):
+        def __init__(self, b):
+            pass
+
+        def load(self, obs, ref, tape):
+            self.got = (obs, ref, tape)
+    sr = par.ShardedRollout(R, 8, 5, 3, torch.device('cpu'))
+    sr.scatter(torch.zeros((8, 5)), None, None, has_ref=False, has_tape=False)
+    assert sr.runner.got[0].shape == (8, 5) and sr.runner.got[1] is None and sr.runner.got[2] is None
