@@ -504,7 +504,7 @@ def run_ours(args):
                 e_.record(torch.cuda.current_stream())
             ks = max(3, min(K, 10))
             ms_s = timed(step, 2, ks, after=lambda: torch.cuda.current_stream().wait_stream(comm))
-            scatter_bytes = int(Bg * (sr.runner.obs0.stride(0) * 4 + 4 + H * 8))
+            scatter_bytes = int(world * sr.runner.inbox.numel() * 4)
             out = {'value': Bg * H * ks / (ms_s / 1e3), 'unit': 'env-steps/s', 'ms_per_step': ms_s / ks,
                    'global_batch': Bg, 'scatter_bytes_per_step': scatter_bytes, 'gather_bytes_per_step': int(Bg * 20),
                    'root_egress_gbs': scatter_bytes * (world - 1) / world / (ms_s / ks / 1e3) / 1e9,

@@ -130,9 +130,9 @@ class ShardedRollout(object):
 
     # -- staged path: views straight into the runners' static buffers -----------------------------
     def stage(self, obses, ref_indexes, tape):
-        """On the source rank: the global batch as (padded observation rows [B, ld] in one allocation,
-        [B] int32 path indexes, action tape [W, H, b, 2] blocked by rank).  One-time layout work, outside
-        the per-rollout exchange."""
+        """On the source rank: the global batch as one buffer of W per-rank blocks, each laid out like a
+        runner's `inbox` (padded observation rows | action tape [H, b, 2] | path indexes).  One-time layout
+        work, outside the per-rollout exchange."""
         import numpy as np
         from .dynamics_and_models import padded_rows
 
@@ -144,29 +144,26 @@ class ShardedRollout(object):
             raise ValueError('the staged scatter needs B %% world_size == 0 (B=%d, W=%d)' % (B, W))
         b = B // W
         r = self.runner
+        n_in = r.inbox.numel()
         ld, off = r.obs0.stride(0), r.obs0.storage_offset()
-        g = padded_rows(B, self.D, r.model._veh_off, self.device)
-        assert g.stride(0) == ld and g.storage_offset() == off
-        g.copy_(to_device(obses))
-        ref = to_device(ref_indexes, torch.int32).reshape(B).contiguous()
-        tp = to_device(tape).reshape(self.H, W, b, 2).permute(1, 0, 2, 3).contiguous()
-        return StagedBatch(g._base, ref, tp, b, ld)
+        n_obs = n_in - self.H * b * 2 - b
+        out = torch.zeros((W, n_in), dtype=torch.float32, device=self.device)
+        obs, ref, tp = to_device(obses), to_device(ref_indexes, torch.int32).reshape(B), to_device(tape)
+        for k in range(W):
+            blk = out[k]
+            blk.as_strided((b, self.D), (ld, 1), blk.storage_offset() + off).copy_(obs[k * b:(k + 1) * b])
+            blk[n_obs:n_obs + self.H * b * 2].view(self.H, b, 2).copy_(tp[:, k * b:(k + 1) * b])
+            blk[n_obs + self.H * b * 2:].view(torch.int32).copy_(ref[k * b:(k + 1) * b])
+        return StagedBatch(out, None, None, b, ld)
 
     def scatter_staged(self, staged=None, slot=0, src=0):
-        """Three collectives whose send buffers are views of the staged batch and whose receive buffers
-        are the runner's own static buffers (RolloutGraph.obs0 / .ref / .tape)."""
+        """ONE collective: the send buffers are the rows of the staged batch, the receive buffer is the
+        runner's own inbox (RolloutGraph.obs0 / .tape / .ref are views of it)."""
         r = self.runners[slot]
-        b, ld = r.B, r.obs0.stride(0)
-        store = r.obs0._base[:b * ld]
         if self.world == 1:
-            store.copy_(staged.obs_store[:b * ld])
-            r.ref.copy_(staged.ref)
-            r.tape.copy_(staged.tape[0])
+            r.inbox.copy_(staged.obs_store[0])
             return
-        root = self.rank == src
-        dist.scatter(store, list(staged.obs_store[:self.B * ld].split(b * ld)) if root else None, src=src, group=self.group)
-        dist.scatter(r.tape, list(staged.tape.unbind(0)) if root else None, src=src, group=self.group)
-        dist.scatter(r.ref, list(staged.ref.split(b)) if root else None, src=src, group=self.group)
+        dist.scatter(r.inbox, list(staged.obs_store.unbind(0)) if self.rank == src else None, src=src, group=self.group)
 
     def run(self, slot=0):
         self.runners[slot].run()

@@ -43,11 +43,17 @@ class RolloutGraph(object):
         off = model._veh_off
         self.D = off + 4 * V
         dev = torch.device('cuda', torch.cuda.current_device())
-        self.obs0 = padded_rows(B, self.D, off, dev)
+        # the three inputs live in ONE allocation ("inbox": padded observation rows | action tape | path
+        # indexes), so that a sharded caller can deliver all of them with a single collective
+        probe = padded_rows(1, self.D, off, dev)
+        ld, front = probe.stride(0), probe.storage_offset()
+        n_obs = max(B, 1) * ld + 16
+        self.inbox = torch.zeros(n_obs + H * B * 2 + B, dtype=torch.float32, device=dev)
+        self.obs0 = self.inbox[:n_obs].as_strided((B, self.D), (ld, 1), front)
+        self.tape = self.inbox[n_obs:n_obs + H * B * 2].view(H, B, 2)
+        self.ref = self.inbox[n_obs + H * B * 2:].view(torch.int32)
         self.buf = [padded_rows(B, self.D, off, dev) for _ in range(2)]
-        self.tape = torch.zeros((H, B, 2), dtype=torch.float32, device=dev)
         self.out5 = torch.zeros((H, 5, B), dtype=torch.float32, device=dev)
-        self.ref = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.final_obs = _wrap(self.buf[(H - 1) % 2])
         self._graph = None
         self._graph_key, self._graph_path, self._filled_index = None, None, None

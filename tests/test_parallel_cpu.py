@@ -108,9 +108,13 @@ class StaticRunner(OracleRunner):
         OracleRunner.__init__(self, b)
         self.B = b
         self.model = type('M', (), dict(_veh_off=9))()
-        self.obs0 = padded_rows(b, 9 + 4 * V, 9, torch.device('cpu'))
-        self.ref = torch.zeros((b,), dtype=torch.int32)
-        self.tape = torch.zeros((H, b, 2), dtype=torch.float32)
+        probe = padded_rows(1, 9 + 4 * V, 9, torch.device('cpu'))
+        ld, front = probe.stride(0), probe.storage_offset()
+        n_obs = b * ld + 16
+        self.inbox = torch.zeros(n_obs + H * b * 2 + b, dtype=torch.float32)
+        self.obs0 = self.inbox[:n_obs].as_strided((b, 9 + 4 * V), (ld, 1), front)
+        self.tape = self.inbox[n_obs:n_obs + H * b * 2].view(H, b, 2)
+        self.ref = self.inbox[n_obs + H * b * 2:].view(torch.int32)
 
     def run(self):
         self.load(self.obs0.clone(), self.ref, self.tape)
