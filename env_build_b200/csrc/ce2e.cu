@@ -702,13 +702,18 @@ int launch_model_step_pair(const StepParams &P, const DeviceInfo *di, cudaStream
     // measured 6 % faster (117.0 vs 124.6 us at B = 524288).  CE2E_PAIR_BAL=0/1 forces.
     static const int env_bal = getenv("CE2E_PAIR_BAL") ? atoi(getenv("CE2E_PAIR_BAL")) : -1;
     const int force_bal = g_use_tma >= 2 ? g_use_tma - 2 : env_bal;
-    const bool bal = force_bal >= 0 ? force_bal != 0 : n_tiles > 2 * max_blocks * PAIR_PAIRS;
-    void (*kern)(const PairParams) = fast ? (bal ? k_model_step_pair<true, true> : k_model_step_pair<true, false>)
-                                          : (bal ? k_model_step_pair<false, true> : k_model_step_pair<false, false>);
-    static std::atomic<bool> smem_set[64][4];
+    // few vehicles: the reward warp streams both halves (PairParams::solo); measured break-even near V = 12
+    static const int env_solo = getenv("CE2E_PAIR_SOLO_V") ? atoi(getenv("CE2E_PAIR_SOLO_V")) : 12;
+    PP.solo = P.V_in <= env_solo;
+    const bool bal = PP.solo ? false : (force_bal >= 0 ? force_bal != 0 : n_tiles > 2 * max_blocks * PAIR_PAIRS);
+    void (*kern)(const PairParams);
+    if (PP.solo) kern = fast ? k_model_step_pair<true, false, true> : k_model_step_pair<false, false, true>;
+    else if (bal) kern = fast ? k_model_step_pair<true, true, false> : k_model_step_pair<false, true, false>;
+    else kern = fast ? k_model_step_pair<true, false, false> : k_model_step_pair<false, false, false>;
+    static std::atomic<bool> smem_set[64][6];
     int dev = 0;
     CE2E_CUDA(cudaGetDevice(&dev));
-    std::atomic<bool> &set = smem_set[dev & 63][(fast ? 2 : 0) + (bal ? 1 : 0)];
+    std::atomic<bool> &set = smem_set[dev & 63][(fast ? 3 : 0) + (PP.solo ? 2 : (bal ? 1 : 0))];
     if (!set.load(std::memory_order_acquire)) {
         CE2E_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di->max_smem_optin));
         set.store(true, std::memory_order_release);
