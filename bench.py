@@ -535,7 +535,7 @@ def run_ours(args):
                            'the action tape as views of the staged batch, %d-step rollout on every rank, NCCL gather of '
                            'the per-row returns (sum over steps of the five outputs); the scatter of rollout i+1 overlaps '
                            'the kernels of rollout i' % H)
-        if world == 8:
+        if world == 8 or os.environ.get('CE2E_BENCH_CONFIG5') == '1':     # (the switch: exercise this block on fewer GPUs)
             # ---- BASELINE config #5 at its stated size: B = 1 048 576 over 8 GPUs (131 072 rows per GPU)
             B5 = 131072
             _, obs5, ref5, tape5 = make_inputs(B5, 20210315 * 1000 + rank)

@@ -66,6 +66,8 @@ SIGNATURES = {
     'ce2e_env_step': (_i, [_vp, _vp, _vp, _i64, _vp, _c.POINTER(TurnClasses), _i, _i, _i, _vp, _i64, _vp, _vp, _vp,
                            _vp, _i64, _vp]),
     'ce2e_env_reset': (_i, [_vp, _c.c_uint64, _vp, _vp, _i, _vp, _i64, _vp, _vp, _i, _i, _i64, _vp]),
+    'ce2e_env_step_reset': (_i, [_vp, _vp, _vp, _i64, _vp, _c.POINTER(TurnClasses), _i, _i, _i, _vp, _i64, _vp, _vp, _vp,
+                                 _vp, _vp, _c.c_uint64, _vp, _i, _vp, _i64, _vp]),
     'ce2e_philox4x32': (None, [_c.POINTER(_c.c_uint32), _c.POINTER(_c.c_uint32), _c.POINTER(_c.c_uint32)]),
     'ce2e_judge_done': (_i, [_i, _vp, _i64, _vp, _i, _i, _i, _vp, _i64, _vp]),
     'ce2e_veh_predict': (_i, [_vp, _i64, _c.POINTER(TurnClasses), _i, _vp, _i64, _i64, _vp]),

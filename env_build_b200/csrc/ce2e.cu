@@ -1046,6 +1046,123 @@ struct VehicleStream {
     }
 };
 
+// ------------------------------------------------------------------------------------------
+// on-device reset of the batched environment (SURVEY 8f-1; E2E:99-127, E2E:472-499)
+// ------------------------------------------------------------------------------------------
+// CrossroadEnd2end.reset -> _reset_init_state for every row whose done code is non-zero (or for all
+// rows when `done` is NULL): a random waypoint index int(u * span) + 700 on the row's path (span =
+// 1400 / 1700 / 920, E2E:473-478), ego = (v_x = 8 u', 0, 0, x, y, phi of that waypoint) (E2E:480-499),
+// tracking columns = tracking_error_vector of that pose (E2E:293-297).  The reference then asks SUMO
+// for the surrounding traffic (traffic.py:151-195, out of scope); here the V vehicle slots are drawn
+// from the synthetic traffic distribution of SURVEY 8d (10 % within +-8 m of the ego, the rest uniform
+// over the +-65 m map, pushed 30 m away if closer than 6 m; v ~ U(0, 8); heading on a compass
+// direction + ~N(0, 10 deg) as the scaled sum of four uniforms).  All draws are Philox4x32-10 outputs
+// keyed by `seed` at counter (row, episode[row], draw block); episode[row] is incremented.  One thread
+// per row; rows that are not done return at once.
+struct ResetParams {
+    PathView pv;
+    GridView gv;
+    const float *full[CE2E_MAX_PATHS];
+    int task, fixed_path, V, n_future, span;
+    uint32_t seed_lo, seed_hi;
+};
+
+// One vehicle slot of a fresh episode (see k_env_reset): draws of Philox blocks 1 + 2 j and 2 + 2 j.
+__device__ __forceinline__ float4 reset_vehicle(uint32_t i_lo, uint32_t i_hi, uint32_t ep, int j, uint32_t k0, uint32_t k1,
+                                                float x, float y) {
+    const Philox4 a = philox4x32_10(i_lo, i_hi, ep, 1u + 2u * (uint32_t)j, k0, k1);
+    const Philox4 b = philox4x32_10(i_lo, i_hi, ep, 2u + 2u * (uint32_t)j, k0, k1);
+    const bool near = (a.v[0] & 0xffffu) < 6554u;
+    const int quad = (int)((a.v[0] >> 16) & 3u);
+    const float u1 = u01_24(a.v[1]), u2 = u01_24(a.v[2]), u3 = u01_24(a.v[3]);
+    float vx = near ? x + (u1 * 16.0f - 8.0f) : u1 * 130.0f - 65.0f;
+    const float vy = near ? y + (u2 * 16.0f - 8.0f) : u2 * 130.0f - 65.0f;
+    const float dd = sq(vx - x) + sq(vy - y);
+    vx = (dd < 36.0f) ? vx + 30.0f : vx;
+    const float s4 = ((u01_24(b.v[0]) + u01_24(b.v[1])) + u01_24(b.v[2])) + u01_24(b.v[3]);
+    const float base = quad == 0 ? 0.0f : (quad == 1 ? 90.0f : (quad == 2 ? 180.0f : -90.0f));
+    float vphi = base + 10.0f * ((s4 - 2.0f) * 1.73205077648162842f);
+    vphi = (vphi > 180.0f) ? vphi - 360.0f : vphi;
+    vphi = (vphi <= -180.0f) ? vphi + 360.0f : vphi;
+    return make_float4(vx, vy, 8.0f * u3, vphi);
+}
+
+// Ego + tracking columns, path index and red-light flag of row i's next episode (one thread); returns the
+// ego position through x, y and the episode number just consumed through ep.
+__device__ __forceinline__ void reset_ego(const ResetParams &R, int64_t i, int32_t *episode, float *obs, int64_t ld,
+                                          int32_t *ref_idx, int8_t *virtual_red, uint32_t &ep, float &x, float &y) {
+    ep = (uint32_t)episode[i];
+    episode[i] = (int32_t)(ep + 1u);
+    const Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)((uint64_t)i >> 32), ep, 0u, R.seed_lo, R.seed_hi);
+    const int p = R.fixed_path >= 0 ? R.fixed_path : (int)(((uint64_t)r.v[0] * (uint32_t)R.pv.n_paths) >> 32);
+    const int L = R.pv.L[p];
+    int idx = (int)(((uint64_t)r.v[1] * (uint32_t)R.span) >> 32) + 700;         // E2E:473-478
+    idx = idx < L ? idx : L - 1;                                                 // indexs2points clamp, DM:727-728
+    const float *tab = R.full[p];
+    x = tab[idx];
+    y = tab[L + idx];
+    const float phi = tab[2 * (size_t)L + idx];
+    const float v = CE2E_EXP_V * u01_24(r.v[2]);                                 // E2E:482
+    float *o = obs + i * ld;
+    o[0] = v; o[1] = 0.0f; o[2] = 0.0f; o[3] = x; o[4] = y; o[5] = phi;
+    int k0, k1, bi;
+    float best;
+    const float2 *t_xy = R.pv.xy + (size_t)p * R.pv.stride;
+    candidate_range(R.gv, p, (R.pv.N[p] + 1) & ~1, x, y, k0, k1);
+    scan_min(t_xy, k0, k1, x, y, best, bi);
+    tracking_from_index(t_xy, R.pv.phi + (size_t)p * R.pv.stride, L, R.pv.tail[p], R.task, bi, x, y, phi, v,
+                        R.n_future, o + 6);
+    ref_idx[i] = p;
+    if (virtual_red) virtual_red[i] = (int8_t)(u01_24(r.v[3]) > 0.9f);             // E2E:120-124
+}
+
+// The vehicle slots of the rows flagged in `pending` (bit = lane that holds the row's ep / x / y; row =
+// row0 + (lane >> lane_shift)), generated by the whole warp: lane j takes slots j, j + 32, ...
+__device__ __forceinline__ void reset_vehicles(const ResetParams &R, unsigned pending, int lane_shift, int64_t row0,
+                                               uint32_t ep, float x, float y, float *obs, int64_t ld, int lane) {
+    const int veh_off = 6 + 3 * (R.n_future + 1);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const int64_t ri = row0 + (src >> lane_shift);
+        const uint32_t rep = __shfl_sync(0xffffffffu, ep, src);
+        const float rx = __shfl_sync(0xffffffffu, x, src), ry = __shfl_sync(0xffffffffu, y, src);
+        float *veh = obs + ri * ld + veh_off;
+        for (int j = lane; j < R.V; j += 32) {
+            const float4 w = reset_vehicle((uint32_t)ri, (uint32_t)((uint64_t)ri >> 32), rep, j, R.seed_lo, R.seed_hi, rx, ry);
+            if ((reinterpret_cast<uintptr_t>(veh) & 15u) == 0) {
+                reinterpret_cast<float4 *>(veh)[j] = w;
+            } else {
+                veh[4 * j] = w.x; veh[4 * j + 1] = w.y; veh[4 * j + 2] = w.z; veh[4 * j + 3] = w.w;
+            }
+        }
+    }
+}
+
+// A warp owns 32 consecutive rows.  Phase 1, one lane per row: the rows to reset draw their ego state, read
+// the waypoint, project it (tracking columns) and write columns 0 .. veh_off - 1 -- a chain of dependent
+// global loads, so all rows of the warp take it at the same time.  Phase 2, the whole warp per reset row
+// (found with one ballot; ego position and episode number broadcast by shuffle): lane j (j, j + 32, ...)
+// generates vehicle slot j.  (With everything in one thread per row a launch was as slow as ~65 Philox
+// blocks in sequence for V = 32.)
+__global__ void __launch_bounds__(256)
+k_env_reset(const __grid_constant__ ResetParams R, int32_t *__restrict__ episode,
+            const int8_t *__restrict__ done, float *__restrict__ obs, int64_t ld,
+            int32_t *__restrict__ ref_idx, int8_t *__restrict__ virtual_red, uint8_t *__restrict__ done_flag, int64_t B) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+    if (row0 >= B) return;
+    const int64_t i = row0 + lane;
+    const bool todo = i < B && (!done || done[i] != 0);
+    if (done_flag && i < B) done_flag[i] = (uint8_t)todo;
+    const unsigned pending = __ballot_sync(0xffffffffu, todo);
+    if (!pending) return;
+    uint32_t ep = 0;
+    float x = 0.f, y = 0.f;
+    if (todo) reset_ego(R, i, episode, obs, ld, ref_idx, virtual_red, ep, x, y);
+    reset_vehicles(R, pending, 0, row0, ep, x, y, obs, ld, lane);
+}
+
 // CrossroadEnd2end._judge_done (E2E:200-256) on the observation AFTER a step, one thread per row.
 // Order of the checks as in the reference: collision (Traffic.collision_check, traffic.py:263-295,
 // with every surrounding vehicle taken as L x W = 4.8 x 2.0 like the ego), road constraint on the
@@ -1065,11 +1182,20 @@ __device__ __forceinline__ bool feasible_point(int task, float px, float py) {
 // TILED = false: one thread per row, scalar loads (any alignment).  TILED = true: VehicleStream,
 // the collision test branch free (a quarter of the synthetic vehicles sit inside the 10 m gate, so a
 // branch would run for nearly every vehicle with a few live lanes), the two halves OR-ed by shuffle.
-template <bool TILED>
+// RESET (tiled kernel only): the rows that are done start their next episode in the same launch
+// (reset_ego / reset_vehicles above = ce2e_env_reset), and done_flag receives code != 0 as 0 / 1 bytes.
+struct DoneReset {
+    ResetParams R;
+    int32_t *episode, *ref_idx;
+    int8_t *virtual_red;
+    uint8_t *done_flag;
+    float *obs_w;                            // the same rows as `obs`, writable
+};
+template <bool TILED, bool RESET = false>
 __global__ void __launch_bounds__(TILED ? TILED_WARPS * 32 : 128)
 k_env_done(const __grid_constant__ DynConsts K, int task, const float *__restrict__ obs,
            int64_t ld, const float *__restrict__ act_scaled, int V, int veh_off,
-           int v_light, int8_t *__restrict__ done, int64_t B) {
+           int v_light, int8_t *__restrict__ done, int64_t B, const __grid_constant__ DoneReset X) {
     __shared__ __align__(16) float s_veh[TILED ? TILED_WARPS : 1][TILED ? 2 * 32 * 4 * VPL : 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t tile = (int64_t)blockIdx.x * TILED_WARPS + warp;
@@ -1108,7 +1234,7 @@ k_env_done(const __grid_constant__ DynConsts K, int task, const float *__restric
                 hit |= gate & in;
             });
             hit |= (bool)__shfl_xor_sync(0xffffffffu, (int)hit, 1);
-            if (!owner) return;
+            if (!RESET && !owner) return;
         } else {
             for (int j = 0; j < V; ++j) {
                 const float *v = o + veh_off + 4 * j;
@@ -1151,7 +1277,22 @@ k_env_done(const __grid_constant__ DynConsts K, int task, const float *__restric
         else goal = y > CE2E_HALF + 10.0f && x > 0.f && x < CE2E_LW3;
         if (goal) code = 6;
     }
-    done[i] = (int8_t)code;
+    if (!RESET) {
+        done[i] = (int8_t)code;
+        return;
+    }
+    if (owner) {
+        done[i] = (int8_t)code;
+        if (X.done_flag) X.done_flag[i] = (uint8_t)(code != 0);
+    }
+    // the warp's 16 rows have been read completely (vs.run is over): rows that are done restart here
+    const bool todo = owner && code != 0;
+    const unsigned pending = __ballot_sync(0xffffffffu, todo);
+    if (!pending) return;
+    uint32_t ep = 0;
+    float rx = 0.f, ry = 0.f;
+    if (todo) reset_ego(X.R, i, X.episode, X.obs_w, ld, X.ref_idx, X.virtual_red, ep, rx, ry);
+    reset_vehicles(X.R, pending, 1, tile * RPW, ep, rx, ry, X.obs_w, ld, lane);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1498,110 +1639,6 @@ __global__ void k_select_vehicles(const __grid_constant__ SelectSpec spec, int t
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// on-device reset of the batched environment (SURVEY 8f-1; E2E:99-127, E2E:472-499)
-// ------------------------------------------------------------------------------------------
-// CrossroadEnd2end.reset -> _reset_init_state for every row whose done code is non-zero (or for all
-// rows when `done` is NULL): a random waypoint index int(u * span) + 700 on the row's path (span =
-// 1400 / 1700 / 920, E2E:473-478), ego = (v_x = 8 u', 0, 0, x, y, phi of that waypoint) (E2E:480-499),
-// tracking columns = tracking_error_vector of that pose (E2E:293-297).  The reference then asks SUMO
-// for the surrounding traffic (traffic.py:151-195, out of scope); here the V vehicle slots are drawn
-// from the synthetic traffic distribution of SURVEY 8d (10 % within +-8 m of the ego, the rest uniform
-// over the +-65 m map, pushed 30 m away if closer than 6 m; v ~ U(0, 8); heading on a compass
-// direction + ~N(0, 10 deg) as the scaled sum of four uniforms).  All draws are Philox4x32-10 outputs
-// keyed by `seed` at counter (row, episode[row], draw block); episode[row] is incremented.  One thread
-// per row; rows that are not done return at once.
-struct ResetParams {
-    PathView pv;
-    GridView gv;
-    const float *full[CE2E_MAX_PATHS];
-    int task, fixed_path, V, n_future, span;
-    uint32_t seed_lo, seed_hi;
-};
-
-// One vehicle slot of a fresh episode (see k_env_reset): draws of Philox blocks 1 + 2 j and 2 + 2 j.
-__device__ __forceinline__ float4 reset_vehicle(uint32_t i_lo, uint32_t i_hi, uint32_t ep, int j, uint32_t k0, uint32_t k1,
-                                                float x, float y) {
-    const Philox4 a = philox4x32_10(i_lo, i_hi, ep, 1u + 2u * (uint32_t)j, k0, k1);
-    const Philox4 b = philox4x32_10(i_lo, i_hi, ep, 2u + 2u * (uint32_t)j, k0, k1);
-    const bool near = (a.v[0] & 0xffffu) < 6554u;
-    const int quad = (int)((a.v[0] >> 16) & 3u);
-    const float u1 = u01_24(a.v[1]), u2 = u01_24(a.v[2]), u3 = u01_24(a.v[3]);
-    float vx = near ? x + (u1 * 16.0f - 8.0f) : u1 * 130.0f - 65.0f;
-    const float vy = near ? y + (u2 * 16.0f - 8.0f) : u2 * 130.0f - 65.0f;
-    const float dd = sq(vx - x) + sq(vy - y);
-    vx = (dd < 36.0f) ? vx + 30.0f : vx;
-    const float s4 = ((u01_24(b.v[0]) + u01_24(b.v[1])) + u01_24(b.v[2])) + u01_24(b.v[3]);
-    const float base = quad == 0 ? 0.0f : (quad == 1 ? 90.0f : (quad == 2 ? 180.0f : -90.0f));
-    float vphi = base + 10.0f * ((s4 - 2.0f) * 1.73205077648162842f);
-    vphi = (vphi > 180.0f) ? vphi - 360.0f : vphi;
-    vphi = (vphi <= -180.0f) ? vphi + 360.0f : vphi;
-    return make_float4(vx, vy, 8.0f * u3, vphi);
-}
-
-// A warp owns 32 consecutive rows.  Phase 1, one lane per row: the rows to reset draw their ego state, read
-// the waypoint, project it (tracking columns) and write columns 0 .. veh_off - 1 -- a chain of dependent
-// global loads, so all rows of the warp take it at the same time.  Phase 2, the whole warp per reset row
-// (found with one ballot; ego position and episode number broadcast by shuffle): lane j (j, j + 32, ...)
-// generates vehicle slot j.  (With everything in one thread per row a launch was as slow as ~65 Philox
-// blocks in sequence for V = 32.)
-__global__ void __launch_bounds__(256)
-k_env_reset(const __grid_constant__ ResetParams R, int32_t *__restrict__ episode,
-            const int8_t *__restrict__ done, float *__restrict__ obs, int64_t ld,
-            int32_t *__restrict__ ref_idx, int8_t *__restrict__ virtual_red, int64_t B) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
-    if (row0 >= B) return;
-    const int64_t i = row0 + lane;
-    const bool todo = i < B && (!done || done[i] != 0);
-    unsigned pending = __ballot_sync(0xffffffffu, todo);
-    if (!pending) return;
-    uint32_t ep = 0;
-    float x = 0.f, y = 0.f;
-    if (todo) {
-        ep = (uint32_t)episode[i];
-        episode[i] = (int32_t)(ep + 1u);
-        const Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)((uint64_t)i >> 32), ep, 0u, R.seed_lo, R.seed_hi);
-        const int p = R.fixed_path >= 0 ? R.fixed_path : (int)(((uint64_t)r.v[0] * (uint32_t)R.pv.n_paths) >> 32);
-        const int L = R.pv.L[p];
-        int idx = (int)(((uint64_t)r.v[1] * (uint32_t)R.span) >> 32) + 700;         // E2E:473-478
-        idx = idx < L ? idx : L - 1;                                                 // indexs2points clamp, DM:727-728
-        const float *tab = R.full[p];
-        x = tab[idx];
-        y = tab[L + idx];
-        const float phi = tab[2 * (size_t)L + idx];
-        const float v = CE2E_EXP_V * u01_24(r.v[2]);                                 // E2E:482
-        float *o = obs + i * ld;
-        o[0] = v; o[1] = 0.0f; o[2] = 0.0f; o[3] = x; o[4] = y; o[5] = phi;
-        int k0, k1, bi;
-        float best;
-        const float2 *t_xy = R.pv.xy + (size_t)p * R.pv.stride;
-        candidate_range(R.gv, p, (R.pv.N[p] + 1) & ~1, x, y, k0, k1);
-        scan_min(t_xy, k0, k1, x, y, best, bi);
-        tracking_from_index(t_xy, R.pv.phi + (size_t)p * R.pv.stride, L, R.pv.tail[p], R.task, bi, x, y, phi, v,
-                            R.n_future, o + 6);
-        ref_idx[i] = p;
-        if (virtual_red) virtual_red[i] = (int8_t)(u01_24(r.v[3]) > 0.9f);             // E2E:120-124
-    }
-    const int veh_off = 6 + 3 * (R.n_future + 1);
-    while (pending) {
-        const int src = __ffs(pending) - 1;
-        pending &= pending - 1;
-        const int64_t ri = row0 + src;
-        const uint32_t rep = __shfl_sync(0xffffffffu, ep, src);
-        const float rx = __shfl_sync(0xffffffffu, x, src), ry = __shfl_sync(0xffffffffu, y, src);
-        float *veh = obs + ri * ld + veh_off;
-        for (int j = lane; j < R.V; j += 32) {
-            const float4 w = reset_vehicle((uint32_t)ri, (uint32_t)((uint64_t)ri >> 32), rep, j, R.seed_lo, R.seed_hi, rx, ry);
-            if ((reinterpret_cast<uintptr_t>(veh) & 15u) == 0) {
-                reinterpret_cast<float4 *>(veh)[j] = w;
-            } else {
-                veh[4 * j] = w.x; veh[4 * j + 1] = w.y; veh[4 * j + 2] = w.z; veh[4 * j + 3] = w.w;
-            }
-        }
-    }
-}
-
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 int check_task(int task) {
@@ -1621,10 +1658,10 @@ int launch_env_done(int task, const float *obs, int64_t ld, const float *act_sca
     if (V > 0 && aligned16(obs + veh_off) && ld % 4 == 0) {
         const int64_t n_tiles = (B + RPW - 1) / RPW;
         k_env_done<true><<<blocks_for(n_tiles, TILED_WARPS), TILED_WARPS * 32, 0, st>>>(
-            make_dyn_consts(1.0 / 10.0), task, obs, ld, act_scaled, V, veh_off, v_light, done, B);
+            make_dyn_consts(1.0 / 10.0), task, obs, ld, act_scaled, V, veh_off, v_light, done, B, DoneReset());
     } else {
         k_env_done<false><<<blocks_for(B, 128), 128, 0, st>>>(make_dyn_consts(1.0 / 10.0), task, obs, ld, act_scaled,
-                                                             V, veh_off, v_light, done, B);
+                                                             V, veh_off, v_light, done, B, DoneReset());
     }
     return after_launch("k_env_done");
 }
@@ -1960,17 +1997,11 @@ int ce2e_env_step(const ce2e_paths *paths, const int32_t *ref_idx, const float *
                            B, (cudaStream_t)stream);
 }
 
-int ce2e_env_reset(const ce2e_paths *paths, uint64_t seed, int32_t *episode, const int8_t *done, int fixed_path,
-                   float *obs, int64_t ld, int32_t *ref_idx, int8_t *virtual_red, int V, int n_future, int64_t B,
-                   void *stream) {
-    int rc;
-    if ((rc = check_batch(B))) return rc;
-    if (B == 0) return CE2E_OK;
-    if (!paths || !episode || !obs || !ref_idx) return fail(CE2E_ERR_NULL, "NULL argument");
+static int make_reset_params(const ce2e_paths *paths, uint64_t seed, int fixed_path, int V, int n_future, int64_t ld,
+                             ResetParams &R) {
     if (V < 0 || V > CE2E_MAX_VEH || n_future < 0 || ld < 6 + 3 * (n_future + 1) + 4 * V)
         return fail(CE2E_ERR_SHAPE, "bad V / n_future / ld");
     if (fixed_path >= paths->n_paths) return fail(CE2E_ERR_PATH, "fixed_path %d outside [0, %d)", fixed_path, paths->n_paths);
-    ResetParams R;
     memset(&R, 0, sizeof(R));
     R.pv = make_view(paths);
     R.gv = make_grid_view(paths);
@@ -1978,7 +2009,50 @@ int ce2e_env_reset(const ce2e_paths *paths, uint64_t seed, int32_t *episode, con
     R.task = paths->task; R.fixed_path = fixed_path < 0 ? -1 : fixed_path; R.V = V; R.n_future = n_future;
     R.span = paths->task == 0 ? 900 + 500 : (paths->task == 1 ? 1200 + 500 : 420 + 500);    // E2E:473-478
     R.seed_lo = (uint32_t)seed; R.seed_hi = (uint32_t)(seed >> 32);
-    k_env_reset<<<blocks_for((B + 31) / 32, 8), 256, 0, (cudaStream_t)stream>>>(R, episode, done, obs, ld, ref_idx, virtual_red, B);
+    return CE2E_OK;
+}
+
+int ce2e_env_reset(const ce2e_paths *paths, uint64_t seed, int32_t *episode, const int8_t *done, int fixed_path,
+                   float *obs, int64_t ld, int32_t *ref_idx, int8_t *virtual_red, int V, int n_future, int64_t B,
+                   void *stream) {
+    int rc;
+    if ((rc = check_batch(B))) return rc;
+    if (B == 0) return CE2E_OK;
+    if (!paths || !episode || !obs || !ref_idx) return fail(CE2E_ERR_NULL, "NULL argument");
+    ResetParams R;
+    if ((rc = make_reset_params(paths, seed, fixed_path, V, n_future, ld, R))) return rc;
+    k_env_reset<<<blocks_for((B + 31) / 32, 8), 256, 0, (cudaStream_t)stream>>>(R, episode, done, obs, ld, ref_idx, virtual_red,
+                                                                                  nullptr, B);
+    return after_launch("k_env_reset");
+}
+
+int ce2e_env_step_reset(const ce2e_paths *paths, int32_t *ref_idx, const float *obs_in, int64_t ld_in,
+                        const float *act_norm, const ce2e_turn_classes *turn, int V, int n_future, int v_light,
+                        float *obs_out, int64_t ld_out, float *out5, float *dict16, float *act_scaled_out,
+                        int8_t *done_out, uint8_t *done_flag_out, uint64_t seed, int32_t *episode, int fixed_path,
+                        int8_t *virtual_red, int64_t B, void *stream) {
+    if (!paths) return fail(CE2E_ERR_NULL, "paths handle is NULL");
+    if (B > 0 && (!ref_idx || !act_scaled_out || !done_out || !episode)) return fail(CE2E_ERR_NULL, "NULL argument");
+    int rc = model_step_common(paths, paths->task, 0, ref_idx, obs_in, ld_in, act_norm, turn, V, V, n_future,
+                               obs_out, ld_out, out5, dict16, act_scaled_out, B,
+                               F_REWARD | F_NEXT | F_ACT_NORM | F_GYM_EGO, stream);
+    if (rc || B == 0) return rc;
+    const int veh_off = 6 + 3 * (n_future + 1);
+    DoneReset X;
+    memset(&X, 0, sizeof(X));
+    if ((rc = make_reset_params(paths, seed, fixed_path, V, n_future, ld_out, X.R))) return rc;
+    X.episode = episode; X.ref_idx = ref_idx; X.virtual_red = virtual_red; X.done_flag = done_flag_out; X.obs_w = obs_out;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (V > 0 && aligned16(obs_out + veh_off) && ld_out % 4 == 0) {
+        // done logic and the restart of the finished rows in ONE launch
+        const int64_t n_tiles = (B + RPW - 1) / RPW;
+        k_env_done<true, true><<<blocks_for(n_tiles, TILED_WARPS), TILED_WARPS * 32, 0, st>>>(
+            make_dyn_consts(1.0 / 10.0), paths->task, obs_out, ld_out, act_scaled_out, V, veh_off, v_light, done_out, B, X);
+        return after_launch("k_env_done");
+    }
+    if ((rc = launch_env_done(paths->task, obs_out, ld_out, act_scaled_out, V, veh_off, v_light, done_out, B, st))) return rc;
+    k_env_reset<<<blocks_for((B + 31) / 32, 8), 256, 0, st>>>(X.R, episode, done_out, obs_out, ld_out, ref_idx, virtual_red,
+                                                              done_flag_out, B);
     return after_launch("k_env_reset");
 }
 

@@ -232,6 +232,14 @@ class CrossroadEnd2end(object):
         host synchronisation: capturable."""
         b = self._bufs
         obs, nxt = b['obs'][cur], b['obs'][1 - cur]
+        if self.auto_reset and self.num_envs > 1 and self.traffic_init is None:
+            fixed = -1 if self._fixed_path is None else int(self._fixed_path)
+            _lib.check(_lib.load().ce2e_env_step_reset(
+                self.ref_path.handle, _ptr(b['ref']), _ptr(obs), obs.stride(0), _ptr(b['act']), ctypes.byref(self._turn),
+                self.veh_num, int(self.num_future_data), int(self.v_light), _ptr(nxt), nxt.stride(0), _ptr(b['out5']),
+                _ptr(b['d16']), _ptr(b['scaled']), _ptr(b['done']), _ptr(b['done_flag']), ctypes.c_uint64(self._seed),
+                _ptr(b['episode']), fixed, _ptr(b['red']), self.num_envs, _stream()))
+            return
         _lib.check(_lib.load().ce2e_env_step(self.ref_path.handle, _ptr(b['ref']), _ptr(obs), obs.stride(0),
                                              _ptr(b['act']), ctypes.byref(self._turn), self.veh_num,
                                              int(self.num_future_data), int(self.v_light), _ptr(nxt), nxt.stride(0),

@@ -196,6 +196,18 @@ int ce2e_env_reset(const ce2e_paths *paths, uint64_t seed, int32_t *episode, con
                    int fixed_path, float *obs, int64_t ld, int32_t *ref_idx, int8_t *virtual_red, int V,
                    int n_future, int64_t B, void *stream);
 
+/* CrossroadEnd2end.step (E2E:132-144) with the reference's `done -> reset()` loop folded in (E2E:99-127):
+ * ce2e_env_step followed by ce2e_env_reset of the rows whose done code is non-zero, as two launches (fused
+ * model step; done logic + restart).  ref_idx is read by the step and rewritten for the restarted rows;
+ * done_out keeps the codes of the step just taken, done_flag_out ([B] bytes 0 / 1, or NULL) = code != 0;
+ * obs_out holds the next observation, or the first observation of the next episode for restarted rows.
+ * Arguments as in ce2e_env_step and ce2e_env_reset.  No host synchronisation: capturable.          */
+int ce2e_env_step_reset(const ce2e_paths *paths, int32_t *ref_idx, const float *obs_in, int64_t ld_in,
+                        const float *act_norm, const ce2e_turn_classes *turn, int V, int n_future, int v_light,
+                        float *obs_out, int64_t ld_out, float *out5, float *dict16, float *act_scaled_out,
+                        int8_t *done_out, uint8_t *done_flag_out, uint64_t seed, int32_t *episode, int fixed_path,
+                        int8_t *virtual_red, int64_t B, void *stream);
+
 /* HOST function: one Philox4x32-10 block, the generator behind ce2e_env_reset's draws (E2E:473, E2E:482
  * use np.random.random()), exported so that tests can pin it against known-answer vectors.        */
 void ce2e_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
