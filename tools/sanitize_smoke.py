@@ -24,6 +24,16 @@ for task in ('left', 'right'):
                 res = m.rollout_out(syn.make_actions(rng, 1, B)[0])
             m.compute_rewards(obs, np.zeros((B, 2), np.float32))
             m.ss(obs, np.zeros((B, 2), np.float32))
+# the TMA pair kernel's other work splits (balanced: chosen for many tiles per pair; forced here), several tiles per pair
+from env_build_b200 import _lib
+for mode_tma, B in ((3, 2100), (2, 2100), (1, 70000)):
+    old = _lib.set_tma(mode_tma)
+    m = EnvironmentModel('left', mode='training', veh_mode_list=syn.tiled_mode_list(VEHICLE_MODE_LIST['left'], 32))
+    ref = syn.make_ref_indexes(rng, B, out_of_range_frac=0.05)
+    m.reset(syn.make_obs(rng, B, 'left', 32, m.ref_path.path_list, ref), ref)
+    for _ in range(2):
+        m.rollout_out(syn.make_actions(rng, 1, B)[0])
+    _lib.set_tma(old)
 env = CrossroadEnd2end('straight', num_envs=777, auto_reset=True)
 env.reset()
 for _ in range(3):
