@@ -512,7 +512,20 @@ def run_ours(args):
             per-row returns.  Two buffer sets per rank: the next rollout's scatter runs on a side stream under
             the current rollout's kernels."""
             Bg = world * Bper
-            sr = ShardedRollout(lambda b: RolloutGraph(model, b, V, H), Bg, D, H, dev, slots=2)
+            # transport of the staged batch: copy-engine pulls over NVLink peer mappings when the box offers
+            # them (every rank must agree), else NCCL's scatter
+            sr, exchange = None, os.environ.get('CE2E_EXCHANGE', 'peer')
+            if exchange == 'peer':
+                try:
+                    sr = ShardedRollout(lambda b: RolloutGraph(model, b, V, H), Bg, D, H, dev, slots=2, exchange='peer')
+                except Exception as e:                                   # noqa: BLE001
+                    print('[bench] peer exchange unavailable on rank %d: %s' % (rank, str(e)[:200]), file=sys.stderr)
+                agree = torch.tensor([int(sr is not None)], device=dev)
+                dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+                if not int(agree):
+                    sr, exchange = None, 'nccl'
+            if sr is None:
+                sr = ShardedRollout(lambda b: RolloutGraph(model, b, V, H), Bg, D, H, dev, slots=2)
             staged = None
             if rank == 0:
                 _, g_obs, g_ref, g_tape = make_inputs(Bg, 4242)
@@ -550,6 +563,9 @@ def run_ours(args):
             ms_s = timed(step, 2, ks, after=lambda: torch.cuda.current_stream().wait_stream(comm))
             scatter_bytes = int(world * sr.runner.inbox.numel() * 4)
             out = {'value': Bg * H * ks / (ms_s / 1e3), 'unit': 'env-steps/s', 'ms_per_step': ms_s / ks,
+                   'exchange': {'peer': 'peer pull: every rank copies its block out of rank 0\'s NVLink-mapped staged '
+                                        'batch with the copy engines (no send/recv kernels)',
+                                'nccl': 'NCCL scatter'}[exchange],
                    'global_batch': Bg, 'scatter_bytes_per_step': scatter_bytes, 'gather_bytes_per_step': int(Bg * 20),
                    'root_egress_gbs': scatter_bytes * (world - 1) / world / (ms_s / ks / 1e3) / 1e9,
                    'nvlink_per_direction_gbs': {'nominal': 900, 'measured_peer_copy': 770}}
@@ -575,10 +591,10 @@ def run_ours(args):
 
         sharded = sharded_leg(B, True)
         sharded['vs_exchange_free'] = sharded['value'] / value
-        sharded['note'] = ('global batch resident on rank 0: NCCL scatter of observations (padded rows), path indexes and '
-                           'the action tape as views of the staged batch, %d-step rollout on every rank, NCCL gather of '
-                           'the per-row returns (sum over steps of the five outputs); the scatter of rollout i+1 overlaps '
-                           'the kernels of rollout i' % H)
+        sharded['note'] = ('global batch resident on rank 0 in scatter-ready layout (padded observation rows, action tape, '
+                           'path indexes per rank block); per rollout: the exchange named in "exchange" into the ranks\' '
+                           'static buffers, %d-step rollout on every rank, NCCL gather of the per-row returns (sum over '
+                           'steps of the five outputs); the exchange of rollout i+1 overlaps the kernels of rollout i' % H)
         if world == 8 or os.environ.get('CE2E_BENCH_CONFIG5') == '1':     # (the switch: exercise this block on fewer GPUs)
             # ---- BASELINE config #5 at its stated size: B = 1 048 576 over 8 GPUs (131 072 rows per GPU)
             B5 = 131072

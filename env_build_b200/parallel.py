@@ -15,6 +15,12 @@ Two ways to feed a `ShardedRollout`:
   by rank), so the collectives send VIEWS of it straight into those buffers: no pad, no copy, no
   permute on either side.  Needs B % world_size == 0.  With `slots=2` the next rollout's inputs can
   travel (on a side stream) while the current one computes.
+
+The staged exchange has two transports.  `exchange='nccl'`: one `dist.scatter` (send / recv kernels, which
+need SMs the persistent step kernel fills).  `exchange='peer'`: the staged batch lives in a buffer that every
+rank of the box maps (torch symmetric memory: CUDA VMM allocations exported over NVLink peer mappings), and
+every rank PULLS its block into its inbox with the copy engines -- no kernel on any SM but a one-block
+barrier, and the source's NVLink egress runs at the peer-copy rate instead of NCCL's send rate.
 """
 import torch
 import torch.distributed as dist
@@ -103,7 +109,10 @@ class ShardedRollout(object):
     returns sum_t out5[t] as [B, 5].  `slots` runners per rank allow one rollout's exchange to overlap
     another's compute."""
 
-    def __init__(self, make_runner, B, D, H, device, group=None, slots=1):
+    def __init__(self, make_runner, B, D, H, device, group=None, slots=1, exchange='nccl', src=0):
+        """exchange='peer' (CUDA, one box, B % world_size == 0; collective: every rank constructs it): the
+        staged batch of rank `src` is pulled over peer mappings, see the module docstring.  Every rank maps a
+        window of the staged batch's size (only `src`'s is read)."""
         self.B, self.D, self.H, self.device, self.group = int(B), int(D), int(H), device, group
         W, rank = _group_info(group)
         self.world, self.rank = W, rank
@@ -112,6 +121,19 @@ class ShardedRollout(object):
         self.runners = [make_runner(hi - lo) for _ in range(int(slots))]
         self.runner = self.runners[0]
         self._gather_out = {}
+        if exchange not in ('nccl', 'peer'):
+            raise ValueError("exchange is 'nccl' or 'peer'")
+        self.exchange, self.src = exchange, int(src)
+        self._window = self._peer = self._src_blocks = None
+        if exchange == 'peer' and W > 1:
+            if B % W:
+                raise ValueError('the staged scatter needs B %% world_size == 0 (B=%d, W=%d)' % (B, W))
+            import torch.distributed._symmetric_memory as symm
+            n_in = self.runner.inbox.numel()
+            self._window = symm.empty(W * n_in, dtype=torch.float32, device=device)
+            name = (group if group is not None else dist.group.WORLD).group_name
+            self._peer = symm.rendezvous(self._window, name)
+            self._src_blocks = self._peer.get_buffer(self.src, (W, n_in), torch.float32)
 
     # -- generic path -------------------------------------------------------------------------
     def scatter(self, obses=None, ref_indexes=None, tape=None, src=0, slot=0, has_ref=True, has_tape=True):
@@ -147,7 +169,12 @@ class ShardedRollout(object):
         n_in = r.inbox.numel()
         ld, off = r.obs0.stride(0), r.obs0.storage_offset()
         n_obs = n_in - self.H * b * 2 - b
-        out = torch.zeros((W, n_in), dtype=torch.float32, device=self.device)
+        if self._window is not None:
+            if self.rank != self.src:
+                raise ValueError('stage() runs on the source rank (%d)' % self.src)
+            out = self._window.view(W, n_in).zero_()
+        else:
+            out = torch.zeros((W, n_in), dtype=torch.float32, device=self.device)
         obs, ref, tp = to_device(obses), to_device(ref_indexes, torch.int32).reshape(B), to_device(tape)
         for k in range(W):
             blk = out[k]
@@ -162,6 +189,15 @@ class ShardedRollout(object):
         r = self.runners[slot]
         if self.world == 1:
             r.inbox.copy_(staged.obs_store[0])
+            return
+        if self._peer is not None:
+            # stream-ordered barrier over the peer mappings (one block): the source's staging writes precede it,
+            # every rank's pull follows it.  The gather of the returns tells the source when the window may be
+            # overwritten.  The pull itself is a device-to-device copy whose source is NVLink-mapped memory.
+            if src != self.src:
+                raise ValueError('the window belongs to rank %d' % self.src)
+            self._peer.barrier(channel=slot)
+            r.inbox.copy_(self._src_blocks[self.rank], non_blocking=True)
             return
         dist.scatter(r.inbox, list(staged.obs_store.unbind(0)) if self.rank == src else None, src=src, group=self.group)
 
