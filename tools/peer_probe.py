@@ -2,8 +2,7 @@
 """Copy-engine exchange probe: how fast can the ranks PULL their block out of rank 0's memory (or rank 0
 PUSH it) with plain cudaMemcpyAsync over a peer mapping, no NCCL kernels on the SMs?
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/peer_probe.py [MB per rank]
-Two mappings are tried: torch's symmetric memory and raw CUDA IPC handles of a cudaMalloc'ed buffer."""
-import ctypes
+The mapping is torch's symmetric memory (CUDA VMM handles); raw cudaIpcOpenMemHandle fails in this container."""
 import os
 import sys
 
@@ -82,43 +81,5 @@ try:
     report('symm push (rank 0, one stream each)', timed(push))
 except Exception as e:                                                  # noqa: BLE001
     print('[rank %d] symmetric memory unavailable: %s: %s' % (rank, type(e).__name__, str(e)[:300]), flush=True)
-
-# ---- raw CUDA IPC
-try:
-    rt = None
-    for line in open('/proc/self/maps'):
-        if 'libcudart' in line:
-            rt = ctypes.CDLL(line.split()[-1])
-            break
-    assert rt is not None, 'libcudart not mapped'
-    ptr = ctypes.c_void_p()
-    assert rt.cudaMalloc(ctypes.byref(ptr), ctypes.c_size_t(world * n * 4)) == 0
-    handle = (ctypes.c_ubyte * 64)()
-    assert rt.cudaIpcGetMemHandle(ctypes.byref(handle), ptr) == 0
-    mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
-    allh = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(allh, mine)
-    if rank == 0:
-        rt.cudaMemcpy(ptr, ctypes.c_void_p(src.data_ptr()), ctypes.c_size_t(world * n * 4), 3)
-    torch.cuda.synchronize(); dist.barrier()
-    if rank != 0:
-        h0 = (ctypes.c_ubyte * 64)(*allh[0].cpu().tolist())
-        rp = ctypes.c_void_p()
-        rc = rt.cudaIpcOpenMemHandle(ctypes.byref(rp), h0, ctypes.c_uint(1))
-        assert rc == 0, 'cudaIpcOpenMemHandle rc=%d' % rc
-    rt.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
-
-    def ipc_pull():
-        if rank != 0:
-            rc = rt.cudaMemcpyAsync(dst.data_ptr(), rp.value + rank * n * 4, n * 4, 4,
-                                    torch.cuda.current_stream().cuda_stream)
-            assert rc == 0, rc
-    report('ipc pull (each rank its block)', timed(ipc_pull))
-    ok = bool(rank == 0 or torch.equal(dst, torch.arange(rank * n, (rank + 1) * n, dtype=torch.float32, device=dev)))
-    flag = torch.tensor([int(ok)], device=dev)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    say('ipc pull content', 'ok' if int(flag) else 'WRONG')
-except Exception as e:                                                  # noqa: BLE001
-    print('[rank %d] raw ipc unavailable: %s: %s' % (rank, type(e).__name__, str(e)[:300]), flush=True)
 
 dist.destroy_process_group()
