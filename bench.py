@@ -497,8 +497,8 @@ def run_ours(args):
         n_env = 100
         ms_env = timed(lambda: [env.step(a_env) for _ in range(n_env)], 1, 3)
         env_rec = {'us_per_step': 1e3 * ms_env / (3 * n_env), 'value': B * 3 * n_env / (ms_env / 1e3), 'unit': 'env-steps/s',
-                   'note': 'CrossroadEnd2end(num_envs=%d, veh_num=%d, auto_reset=True, use_graph=True).step(): three '
-                           'kernels per step (k_model_step_pair, k_env_done, k_env_reset) in one graph replay, Python '
+                   'note': 'CrossroadEnd2end(num_envs=%d, veh_num=%d, auto_reset=True, use_graph=True).step(): two '
+                           'kernels per step (k_model_step_pair; k_env_done = done logic + restart of finished rows) in one graph replay, Python '
                            'call included' % (B, V)}
         del env
     # ---- N > 1: the batch lives on rank 0; NCCL scatters the row blocks and gathers the returns

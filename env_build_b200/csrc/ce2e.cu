@@ -1044,6 +1044,25 @@ struct VehicleStream {
         }
         cp_async_wait<0>();
     }
+    // f(float4 vehicle, bool valid) for every slot of every chunk, the whole warp converged in every call
+    // (valid = the slot holds a vehicle of this lane's half), so f may use warp collectives
+    template <class F>
+    __device__ __forceinline__ void run_all(F &&f) const {
+        const int h = lane & 1, swz = (lane >> 1) & 3;
+        const int j_end = h ? V : min(H, V);
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            if (ch + 1 < n_chunks) stage(ch + 1, (ch + 1) & 1);
+            else cp_async_commit();
+            cp_async_wait<1>();
+            __syncwarp();
+            const float4 *slot = reinterpret_cast<const float4 *>(buf + (ch & 1) * (32 * 4 * VPL) + lane * (4 * VPL));
+            const int j0 = h * H + ch * VPL;
+#pragma unroll
+            for (int e = 0; e < VPL; ++e) f(slot[e ^ swz], j0 + e < j_end);
+            __syncwarp();
+        }
+        cp_async_wait<0>();
+    }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1197,16 +1216,20 @@ k_env_done(const __grid_constant__ DynConsts K, int task, const float *__restric
            int64_t ld, const float *__restrict__ act_scaled, int V, int veh_off,
            int v_light, int8_t *__restrict__ done, int64_t B, const __grid_constant__ DoneReset X) {
     __shared__ __align__(16) float s_veh[TILED ? TILED_WARPS : 1][TILED ? 2 * 32 * 4 * VPL : 4];
+    __shared__ float4 s_gate[TILED ? TILED_WARPS : 1][TILED ? 64 : 1];      // vehicles inside the gate, per warp
+    __shared__ float4 s_ego[TILED ? TILED_WARPS : 1][TILED ? RPW : 1];      // the rows' ego circle centres
+    __shared__ int s_hit[TILED ? TILED_WARPS : 1][TILED ? RPW : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t tile = (int64_t)blockIdx.x * TILED_WARPS + warp;
     int64_t i;
-    bool owner = true;
+    bool owner = true, live = true;
     VehicleStream vs;
     if (TILED) {
         if (tile * RPW >= B) return;         // whole warp
         const int64_t row = tile * RPW + (lane >> 1);
-        owner = row < B && (lane & 1) == 0;
-        i = row < B ? row : B - 1;
+        live = row < B;
+        owner = live && (lane & 1) == 0;
+        i = live ? row : B - 1;
         vs.init(s_veh[warp], obs, ld, veh_off, V, tile, B, lane);
         vs.begin();
     } else {
@@ -1224,16 +1247,46 @@ k_env_done(const __grid_constant__ DynConsts K, int task, const float *__restric
         const float thr = 6.25f;
         bool hit = false;
         if (TILED) {
-            vs.run([&](float4 v) {
+            // Few vehicles are inside the 10 m gate, but nearly every warp has some lane with one: the lanes
+            // only test the gate and push the vehicles that pass into a warp-shared ring; whenever it holds 32,
+            // every lane takes one (heading sin / cos, circle centres, the four distances).  The result is an OR
+            // over the row's vehicles, so the order does not matter.
+            const int rloc = lane >> 1;
+            if ((lane & 1) == 0) {
+                s_ego[warp][rloc] = make_float4(e.fx, e.fy, e.rx, e.ry);
+                s_hit[warp][rloc] = 0;
+            }
+            __syncwarp();
+            int head = 0, count = 0;                                       // warp-uniform
+            auto take = [&](int k) {
+                const float4 q = s_gate[warp][k & 63];
+                const int r = __float_as_int(q.w);
+                const float4 eg = s_ego[warp][r];
                 float ws, wc;
-                sincos_cw(deg2rad(v.w), ws, wc);
-                const Circles w = circle_centres(v.x, v.y, ws, wc);
-                const bool gate = fabsf(v.x - x) < 10.0f && fabsf(v.y - y) < 10.0f;
-                const bool in = (sq(e.fx - w.fx) + sq(e.fy - w.fy) < thr) | (sq(e.fx - w.rx) + sq(e.fy - w.ry) < thr) |
-                                (sq(e.rx - w.rx) + sq(e.ry - w.ry) < thr) | (sq(e.rx - w.fx) + sq(e.ry - w.fy) < thr);
-                hit |= gate & in;
+                sincos_cw(deg2rad(q.z), ws, wc);
+                const Circles w = circle_centres(q.x, q.y, ws, wc);
+                const bool in = (sq(eg.x - w.fx) + sq(eg.y - w.fy) < thr) | (sq(eg.x - w.rx) + sq(eg.y - w.ry) < thr) |
+                                (sq(eg.z - w.rx) + sq(eg.w - w.ry) < thr) | (sq(eg.z - w.fx) + sq(eg.w - w.fy) < thr);
+                if (in) s_hit[warp][r] = 1;
+            };
+            vs.run_all([&](float4 v, bool valid) {
+                const bool gate = valid && live && fabsf(v.x - x) < 10.0f && fabsf(v.y - y) < 10.0f;
+                const unsigned m = __ballot_sync(0xffffffffu, gate);
+                if (gate)
+                    s_gate[warp][(head + count + __popc(m & ((1u << lane) - 1u))) & 63] =
+                        make_float4(v.x, v.y, v.w, __int_as_float(rloc));
+                count += __popc(m);
+                if (count >= 32) {
+                    __syncwarp();
+                    take(head + lane);
+                    head += 32; count -= 32;
+                    __syncwarp();
+                }
             });
-            hit |= (bool)__shfl_xor_sync(0xffffffffu, (int)hit, 1);
+            __syncwarp();
+            if (lane < count) take(head + lane);
+            __syncwarp();
+            hit = s_hit[warp][rloc] != 0;
             if (!RESET && !owner) return;
         } else {
             for (int j = 0; j < V; ++j) {
