@@ -98,7 +98,7 @@ class CrossroadEnd2end(object):
         self.reward_info_enabled = bool(reward_info)     # the 16-term reward dict triples the step's writes
         self.use_graph = bool(use_graph)                 # replay step() as a CUDA graph (batched, device reset)
         self._bufs = None                                # static state, allocated by reset()
-        self._graphs = [None, None]
+        self._graphs, self._act_seen = {}, {}
         self._views, self._cur_obs = {}, None
         self.v_light = 0                     # the model traffic has no signal phases: always green
         self.done_type = 'not_done_yet'
@@ -117,7 +117,7 @@ class CrossroadEnd2end(object):
         return [seed]
 
     def close(self):
-        self._graphs = [None, None]
+        self._graphs, self._act_seen = {}, {}
         self.ref_path.close()
 
     def set_traj(self, trajectory):
@@ -127,7 +127,7 @@ class CrossroadEnd2end(object):
         (hier_decision.py:115-124, multi_ego.py:104)."""
         self.ref_path = trajectory
         self.env_model.ref_path = trajectory
-        self._graphs = [None, None]                      # captured steps hold the old table handle
+        self._graphs, self._act_seen = {}, {}                      # captured steps hold the old table handle
         if self.obs is not None:
             self.ref_indexes.fill_(int(trajectory.ref_index))
             self._fill_tracking(self.obs, self.ref_indexes)
@@ -197,7 +197,7 @@ class CrossroadEnd2end(object):
     def reset(self, **kwargs):
         """E2E:99-127.  Batched environments draw their path per row; `reset(ref_index=k)` (the
         reference's ReferencePath kwargs) pins every row to path k."""
-        self._graphs = [None, None]
+        self._graphs, self._act_seen = {}, {}
         if kwargs:
             self.ref_path = ReferencePath(self.training_task, **kwargs)      # E2E:100
             self.env_model.ref_path = self.ref_path
@@ -226,22 +226,24 @@ class CrossroadEnd2end(object):
         return self._squeeze(self.obs)
 
     # -- step -------------------------------------------------------------------------------------
-    def _enqueue_step(self, cur):
+    def _enqueue_step(self, cur, act=None):
         """One environment step on the static buffers: the fused model step + done kernel
         (ce2e_env_step) and, with auto_reset on the device path, the reset kernel.  No allocation, no
-        host synchronisation: capturable."""
+        host synchronisation: capturable.  `act`: device pointer of the [B, 2] actions (default: the
+        action buffer)."""
         b = self._bufs
         obs, nxt = b['obs'][cur], b['obs'][1 - cur]
+        act = _ptr(b['act']) if act is None else act
         if self.auto_reset and self.num_envs > 1 and self.traffic_init is None:
             fixed = -1 if self._fixed_path is None else int(self._fixed_path)
             _lib.check(_lib.load().ce2e_env_step_reset(
-                self.ref_path.handle, _ptr(b['ref']), _ptr(obs), obs.stride(0), _ptr(b['act']), ctypes.byref(self._turn),
+                self.ref_path.handle, _ptr(b['ref']), _ptr(obs), obs.stride(0), act, ctypes.byref(self._turn),
                 self.veh_num, int(self.num_future_data), int(self.v_light), _ptr(nxt), nxt.stride(0), _ptr(b['out5']),
                 _ptr(b['d16']), _ptr(b['scaled']), _ptr(b['done']), _ptr(b['done_flag']), ctypes.c_uint64(self._seed),
                 _ptr(b['episode']), fixed, _ptr(b['red']), self.num_envs, _stream()))
             return
         _lib.check(_lib.load().ce2e_env_step(self.ref_path.handle, _ptr(b['ref']), _ptr(obs), obs.stride(0),
-                                             _ptr(b['act']), ctypes.byref(self._turn), self.veh_num,
+                                             act, ctypes.byref(self._turn), self.veh_num,
                                              int(self.num_future_data), int(self.v_light), _ptr(nxt), nxt.stride(0),
                                              _ptr(b['out5']), _ptr(b['d16']), _ptr(b['scaled']), _ptr(b['done']),
                                              self.num_envs, _stream()))
@@ -265,7 +267,7 @@ class CrossroadEnd2end(object):
             self._views[cur] = v
         return v
 
-    def _capture(self, cur):
+    def _capture(self, cur, act=None):
         b = self._bufs
         self.ref_path.handle                   # create the device tables outside the capture
         state = (b['obs'][0], b['obs'][1], b['episode'], b['ref'])
@@ -273,28 +275,47 @@ class CrossroadEnd2end(object):
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             snap = [t.clone() for t in state]
-            self._enqueue_step(cur)            # warm-up outside the capture, then undo its effects
+            self._enqueue_step(cur, act)       # warm-up outside the capture, then undo its effects
             for t, c in zip(state, snap):
                 t.copy_(c)
         torch.cuda.current_stream().wait_stream(s)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._enqueue_step(cur)
-        self._graphs[cur] = g
+            self._enqueue_step(cur, act)
+        if len(self._graphs) >= 8:             # callers that keep changing their action tensor: start over
+            self._graphs.clear()
+        self._graphs[(cur, None if act is None else act.value)] = g
 
     def step(self, action):
         """E2E:132-144.  Batched environments return views of static device buffers (observations,
         rewards, done flags, info tensors): they are overwritten by the next step() -- clone what must
         be kept.  With auto_reset the returned observation rows of finished environments are already
         those of their next episode, and `done` still flags them.  `action` may be `env.action_buffer`
-        itself (filled in place by the policy), which saves the copy."""
+        itself (filled in place by the policy), which saves the copy; a contiguous float32 CUDA tensor is
+        read in place too (a graph captured for its address once the same tensor has been passed a few
+        times), anything else is copied into the action buffer."""
         B = self.num_envs
         if self._bufs is None:
             raise RuntimeError('call reset() before step()')
         b = self._bufs
+        graphed = self.use_graph and B > 1 and self.traffic_init is None
+        act_ptr = None                                   # None: the action buffer
         if action is not b['act']:
             act = action if isinstance(action, torch.Tensor) else to_device(np.asarray(action, np.float32))
-            b['act'].copy_(act.reshape(B, 2), non_blocking=True)
+            in_place = (act.is_cuda and act.dtype == torch.float32 and act.is_contiguous() and act.numel() == 2 * B
+                        and act.device == b['act'].device and not act.requires_grad and act.data_ptr() % 8 == 0)
+            if in_place and graphed:
+                # a graph per action address pays off only for a tensor that keeps coming back
+                key = act.data_ptr()
+                seen = self._act_seen.get(key, 0) + 1
+                if len(self._act_seen) > 64:
+                    self._act_seen.clear()
+                self._act_seen[key] = seen
+                in_place = seen >= 3 or (self._cur, key) in self._graphs or (1 - self._cur, key) in self._graphs
+            if in_place:
+                act_ptr = ctypes.c_void_p(act.data_ptr())
+            else:
+                b['act'].copy_(act.reshape(B, 2), non_blocking=True)
         cur = self._cur
         # a caller may have assigned env.obs / env.ref_indexes (the reference's attributes): adopt them
         if self.obs is not self._cur_obs:
@@ -304,12 +325,13 @@ class CrossroadEnd2end(object):
             if self.ref_indexes is not None and self.ref_indexes.data_ptr() != b['ref'].data_ptr():
                 b['ref'].copy_(to_device(self.ref_indexes, torch.int32).reshape(B), non_blocking=True)
             self.ref_indexes = b['ref']
-        if self.use_graph and B > 1 and self.traffic_init is None:
-            if self._graphs[cur] is None:
-                self._capture(cur)
-            self._graphs[cur].replay()
+        if graphed:
+            key = (cur, None if act_ptr is None else act_ptr.value)
+            if key not in self._graphs:
+                self._capture(cur, act_ptr)
+            self._graphs[key].replay()
         else:
-            self._enqueue_step(cur)
+            self._enqueue_step(cur, act_ptr)
         self._cur = cur = 1 - cur
         if B > 1:
             v = self._views_for(cur)

@@ -292,6 +292,34 @@ def test_auto_reset_on_device_in_a_graph(e2e):
     assert (envs[0]._bufs['episode'].cpu().numpy() == episodes + 1).all()
 
 
+def test_actions_read_in_place_from_a_cuda_tensor(e2e):
+    """A policy's own CUDA action tensor passed again and again: after a few steps the env reads it in place
+    (a graph captured for its address, no copy kernel); host arrays and other tensors keep going through the
+    action buffer.  All three ways give identical steps."""
+    task, B, V = 'right', 2048, 5
+    envs = [e2e.CrossroadEnd2end(task, num_envs=B, veh_num=V, auto_reset=True, use_graph=True, reward_info=False)
+            for _ in range(3)]
+    for env in envs:
+        env.seed(3)
+        env.reset()
+    rng = np.random.default_rng(5)
+    mine = torch.empty((B, 2), device='cuda')                    # env 0: the same tensor every step
+    for t in range(12):
+        act = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+        mine.copy_(torch.as_tensor(act))
+        envs[1].action_buffer.copy_(torch.as_tensor(act))         # env 1: the env's own buffer
+        outs = [envs[0].step(mine), envs[1].step(envs[1].action_buffer), envs[2].step(act)]   # env 2: host array
+        for o in outs[1:]:
+            assert torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) and torch.equal(outs[0][2], o[2]), t
+    keys = {k[1] for k in envs[0]._graphs}
+    assert mine.data_ptr() in keys                               # the dedicated graphs exist ...
+    assert {k[1] for k in envs[1]._graphs} == {None}            # (env 2's staging copies may recycle one address)
+    # ... and a tensor seen once does not trigger a capture
+    n = len(envs[0]._graphs)
+    envs[0].step(torch.zeros((B, 2), device='cuda'))
+    assert len(envs[0]._graphs) == n
+
+
 @pytest.mark.parametrize('task', TASKS)
 def test_set_traj_reprojects_tracking(e2e, task):
     """The reference's decision pattern `env.set_traj(path); env._get_obs()` (hier_decision.py:115-124):
