@@ -636,7 +636,10 @@ def run_ours(args):
                 'e2e': {'value': e2e_graph['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': d2h, 'steps': ke,
                         'timing': 'one CUDA-event pair around all steps; H2D, kernels and D2H run on three streams '
-                                  '(two buffer sets), all joined before the end event; median of three such runs',
+                                  '(two buffer sets), all joined before the end event; median of three such runs. The region '
+                                  'starts with an empty pipeline and ends drained: the first H2D + rollout (1.4 ms) is not '
+                                  'overlapped, after that a rollout costs its D2H (1.25 ms alone, ~1.35 ms under the '
+                                  'concurrent H2D)',
                         'runs': e2e_graph['runs'], 'path': e2e_graph['path'],
                         'per_step_api': {'value': e2e_value, 'unit': 'env-steps/s',
                                          'runs': [world * B * H * ke / (m / 1e3) for m in e2e_runs],
