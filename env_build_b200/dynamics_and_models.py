@@ -113,12 +113,14 @@ def _ld(t):
 
 
 def padded_rows(B, D, veh_off, device=None):
-    """An uninitialised [B, D] fp32 view whose rows are padded so that column `veh_off`
-    (the first vehicle) of every row is 64-byte aligned (the kernels need 16 B for their vector
-    path; 64 B makes every staged piece whole 32 B DRAM sectors): row stride is a multiple of 16
-    floats and the view starts (-veh_off) % 16 floats into the allocation."""
+    """An uninitialised [B, D] fp32 view in the row layout the kernels like: the first vehicle column
+    (`veh_off`) of every row is 16-byte aligned (float4 loads, TMA boxes; 64 B for row 0), the row stride is a
+    multiple of 4 floats, and with veh_off == 9 (no preview points) every row is preceded by at least 7
+    floats of padding, so that the 64 B in front of a row's vehicle block (its ego + tracking columns) can
+    travel as one TMA box without touching the previous row's data.  V = 32: 144 floats per row, V = 8 / 9 /
+    5: 48 / 52 / 36."""
     front = (-veh_off) % 16
-    ld = -(-(front + D) // 16) * 16
+    ld = -(-(D + (7 if veh_off == 9 else 0)) // 4) * 4
     store = torch.empty(max(B, 1) * ld + 16, dtype=torch.float32, device=device or _device())
     return store.as_strided((B, D), (ld, 1), front)
 

@@ -46,7 +46,7 @@ def main():
     only_tma = os.environ.get('AB_TMA_ONLY') == '1'          # one column: compare builds across processes
     cfgs = [('left', 65536, 32), ('left', 131072, 32), ('left', 524288, 32), ('left', 65536, 8),
             ('straight', 65536, 9), ('right', 65536, 5), ('left', 4096, 32), ('left', 65536, 12), ('left', 65536, 16),
-            ('left', 65536, 24)]
+            ('left', 65536, 24), ('left', 524288, 8), ('straight', 524288, 9), ('right', 524288, 5), ('left', 262144, 8)]
     if os.environ.get('AB_CONFIGS'):
         cfgs = [cfgs[int(i)] for i in os.environ['AB_CONFIGS'].split(',')]
     print('# k_model_step_pair (TMA) vs k_model_step (cp.async), %s, lib %s\n' % (torch.cuda.get_device_name(0),
