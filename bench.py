@@ -507,17 +507,18 @@ def run_ours(args):
         from env_build_b200.parallel import ShardedRollout
 
         def sharded_leg(Bper, check):
-            """Global batch of world * Bper rows resident on rank 0 in scatter-ready layout; per rollout: NCCL
-            scatter (views of it -> the ranks' static buffers), H-step rollout on every rank, NCCL gather of the
-            per-row returns.  Two buffer sets per rank: the next rollout's scatter runs on a side stream under
-            the current rollout's kernels."""
+            """Global batch of world * Bper rows resident on rank 0 in scatter-ready layout; per rollout: the
+            exchange (blocks of it -> the ranks' static buffers), H-step rollout on every rank, NCCL gather of the
+            per-row returns.  Three buffer sets per rank: the next rollouts' inputs travel on a side stream under
+            the current rollout's kernels.  The timed region is self-contained (pipeline fill included)."""
             Bg = world * Bper
             # transport of the staged batch: copy-engine pulls over NVLink peer mappings when the box offers
             # them (every rank must agree), else NCCL's scatter
             sr, exchange = None, os.environ.get('CE2E_EXCHANGE', 'peer')
+            S = max(2, int(os.environ.get('CE2E_EXCHANGE_SLOTS', '3')))    # buffer sets per rank
             if exchange == 'peer':
                 try:
-                    sr = ShardedRollout(lambda b: RolloutGraph(model, b, V, H), Bg, D, H, dev, slots=2, exchange='peer')
+                    sr = ShardedRollout(lambda b: RolloutGraph(model, b, V, H), Bg, D, H, dev, slots=S, exchange='peer')
                 except Exception as e:                                   # noqa: BLE001
                     print('[bench] peer exchange unavailable on rank %d: %s' % (rank, str(e)[:200]), file=sys.stderr)
                 agree = torch.tensor([int(sr is not None)], device=dev)
@@ -525,16 +526,17 @@ def run_ours(args):
                 if not int(agree):
                     sr, exchange = None, 'nccl'
             if sr is None:
-                sr = ShardedRollout(lambda b: RolloutGraph(model, b, V, H), Bg, D, H, dev, slots=2)
+                sr = ShardedRollout(lambda b: RolloutGraph(model, b, V, H), Bg, D, H, dev, slots=S)
             staged = None
             if rank == 0:
                 _, g_obs, g_ref, g_tape = make_inputs(Bg, 4242)
                 staged = sr.stage(g_obs, g_ref, g_tape)
             for r_ in sr.runners:
                 r_.run()                                  # capture the graphs before any timing
-            comm = torch.cuda.Stream()
-            ready = [torch.cuda.Event() for _ in range(2)]
-            done = [torch.cuda.Event() for _ in range(2)]
+            comm, gath = torch.cuda.Stream(), torch.cuda.Stream()
+            ready = [torch.cuda.Event() for _ in range(S)]
+            done = [torch.cuda.Event() for _ in range(S)]
+            gathered = [torch.cuda.Event() for _ in range(S)]
             ret = {}
             state = {'i': 0}
 
@@ -544,23 +546,35 @@ def run_ours(args):
                     sr.scatter_staged(staged, slot=slot)
                     ready[slot].record(comm)
 
-            def step():
+            def region(n):
+                # n rollouts, self-contained (n exchanges, n rollouts, n gathers; nothing in flight before or after):
+                # rollout i computes on buffer set i % S while the inputs of rollouts i+1 .. i+S-1 travel -- with three
+                # sets the exchange stream always has the next transfer queued behind the current one
                 main = torch.cuda.current_stream()
-                i = state['i']
-                slot = i % 2
-                if i == 0:
-                    issue_scatter(0)
-                issue_scatter(1 - slot)                   # next rollout's inputs travel while this one computes
-                main.wait_event(ready[slot])
-                sr.run(slot=slot)
-                done[slot].record(main)
-                ret['r'] = sr.gather_returns(slot=slot)
-                state['i'] = i + 1
+                for e_ in done + gathered:
+                    e_.record(main)
+                gath.wait_stream(main)
+                for k_ in range(min(S - 1, n)):
+                    issue_scatter(k_)
+                for i in range(n):
+                    slot = i % S
+                    if i + S - 1 < n:
+                        issue_scatter((i + S - 1) % S)
+                    main.wait_event(ready[slot])
+                    main.wait_event(gathered[slot])       # the returns of the rollout that last used this set are out
+                    sr.run(slot=slot)
+                    done[slot].record(main)
+                    with torch.cuda.stream(gath):         # the returns' reduction + gather leave the kernel stream
+                        gath.wait_event(done[slot])
+                        ret['r'] = sr.gather_returns(slot=slot)
+                        gathered[slot].record(gath)
 
-            for e_ in done:
-                e_.record(torch.cuda.current_stream())
-            ks = max(3, min(K, 10))
-            ms_s = timed(step, 2, ks, after=lambda: torch.cuda.current_stream().wait_stream(comm))
+            def join():
+                torch.cuda.current_stream().wait_stream(comm)
+                torch.cuda.current_stream().wait_stream(gath)
+
+            ks = max(6, min(2 * K, 20))
+            ms_s = timed(lambda: region(ks), 1, 1, after=join)
             scatter_bytes = int(world * sr.runner.inbox.numel() * 4)
             out = {'value': Bg * H * ks / (ms_s / 1e3), 'unit': 'env-steps/s', 'ms_per_step': ms_s / ks,
                    'exchange': {'peer': 'peer pull: every rank copies its block out of rank 0\'s NVLink-mapped staged '
@@ -568,7 +582,10 @@ def run_ours(args):
                                 'nccl': 'NCCL scatter'}[exchange],
                    'global_batch': Bg, 'scatter_bytes_per_step': scatter_bytes, 'gather_bytes_per_step': int(Bg * 20),
                    'root_egress_gbs': scatter_bytes * (world - 1) / world / (ms_s / ks / 1e3) / 1e9,
-                   'nvlink_per_direction_gbs': {'nominal': 900, 'measured_peer_copy': 770}}
+                   'nvlink_per_direction_gbs': {'nominal': 900, 'measured_peer_copy': 770, 'measured_pull_7_peers': 835},
+                   'buffer_sets': S, 'rollouts_timed': ks,
+                   'timing': 'one event pair around a self-contained run of rollouts_timed rollouts (first exchange not '
+                             'overlapped), max over ranks'}
             if check:
                 # driver-side NCCL correctness: the gathered returns against a local rollout of the same rows
                 torch.cuda.synchronize()
@@ -594,7 +611,8 @@ def run_ours(args):
         sharded['note'] = ('global batch resident on rank 0 in scatter-ready layout (padded observation rows, action tape, '
                            'path indexes per rank block); per rollout: the exchange named in "exchange" into the ranks\' '
                            'static buffers, %d-step rollout on every rank, NCCL gather of the per-row returns (sum over '
-                           'steps of the five outputs); the exchange of rollout i+1 overlaps the kernels of rollout i' % H)
+                           'steps of the five outputs); three buffer sets per rank: the exchanges of rollouts i+1 and i+2 overlap the '
+                           'kernels of rollout i' % H)
         if world == 8 or os.environ.get('CE2E_BENCH_CONFIG5') == '1':     # (the switch: exercise this block on fewer GPUs)
             # ---- BASELINE config #5 at its stated size: B = 1 048 576 over 8 GPUs (131 072 rows per GPU)
             B5 = 131072
