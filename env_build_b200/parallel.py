@@ -154,7 +154,9 @@ class ShardedRollout(object):
     def stage(self, obses, ref_indexes, tape):
         """On the source rank: the global batch as one buffer of W per-rank blocks, each laid out like a
         runner's `inbox` (padded observation rows | action tape [H, b, 2] | path indexes).  One-time layout
-        work, outside the per-rollout exchange."""
+        work, outside the per-rollout exchange.  With exchange='peer' the blocks are written into the window the
+        other ranks pull from: stage the next batch only after the returns of every rollout that pulled the
+        previous one have been gathered."""
         import numpy as np
         from .dynamics_and_models import padded_rows
 
