@@ -64,7 +64,7 @@ for s_ in np.unique(sm):
     t0[sm == s_] = t[sm == s_, 0].min()
 print('# phase timeline (%s), B=%d V=%d, %d warps traced, clock cycles (1.965 GHz)\n' % ('warm L2' if WARM else 'L2 flushed', B, V, len(t)))
 for r in (0, 1):
-    print('## role %d (%s)\n\n| phase | dur median | p90 | max | end median | end p90 | end max |\n|---|---|---|---|---|---|---|' %
+    print('## role %d (%s)\n\n| phase | dur median | p90 | max | end min | end p10 | end median | end p90 | end max |\n|---|---|---|---|---|---|---|---|---|' %
           (r, 'reward warp, first half' if r == 0 else 'dynamics warp, second half'))
     sel = role == r
     prev = 0
@@ -73,8 +73,8 @@ for r in (0, 1):
             continue
         d = t[sel, k] - t[sel, prev]
         e = t[sel, k] - t0[sel]
-        print('| %s | %d | %d | %d | %d | %d | %d |' % (names[k], np.median(d), np.percentile(d, 90), d.max(), np.median(e),
-                                                      np.percentile(e, 90), e.max()))
+        print('| %s | %d | %d | %d | %d | %d | %d | %d | %d |' % (names[k], np.median(d), np.percentile(d, 90), d.max(), e.min(),
+                                                                np.percentile(e, 10), np.median(e), np.percentile(e, 90), e.max()))
         prev = k
     print()
 span = np.array([t[sm == s_, 14].max() - t[sm == s_, 0].min() for s_ in np.unique(sm)])
