@@ -993,6 +993,11 @@ __global__ void k_ss(const float *__restrict__ obs, int64_t ld, const float *__r
 // aligned vehicle block and ld % 4 == 0.
 // ------------------------------------------------------------------------------------------
 constexpr int TILED_WARPS = 8;
+#ifndef CE2E_DONE_WARPS
+#define CE2E_DONE_WARPS 2
+#endif
+// k_env_done is one partial wave (4096 warps at B = 65 536): small blocks spread it evenly over the SMs
+constexpr int DONE_WARPS = CE2E_DONE_WARPS;
 struct VehicleStream {
     float *buf;                // this warp's 2 x (32 * 4 * VPL) floats
     const float *g_in;
@@ -1211,16 +1216,16 @@ struct DoneReset {
     float *obs_w;                            // the same rows as `obs`, writable
 };
 template <bool TILED, bool RESET = false>
-__global__ void __launch_bounds__(TILED ? TILED_WARPS * 32 : 128)
+__global__ void __launch_bounds__(TILED ? DONE_WARPS * 32 : 128)
 k_env_done(const __grid_constant__ DynConsts K, int task, const float *__restrict__ obs,
            int64_t ld, const float *__restrict__ act_scaled, int V, int veh_off,
            int v_light, int8_t *__restrict__ done, int64_t B, const __grid_constant__ DoneReset X) {
-    __shared__ __align__(16) float s_veh[TILED ? TILED_WARPS : 1][TILED ? 2 * 32 * 4 * VPL : 4];
-    __shared__ float4 s_gate[TILED ? TILED_WARPS : 1][TILED ? 64 : 1];      // vehicles inside the gate, per warp
-    __shared__ float4 s_ego[TILED ? TILED_WARPS : 1][TILED ? RPW : 1];      // the rows' ego circle centres
-    __shared__ int s_hit[TILED ? TILED_WARPS : 1][TILED ? RPW : 1];
+    __shared__ __align__(16) float s_veh[TILED ? DONE_WARPS : 1][TILED ? 2 * 32 * 4 * VPL : 4];
+    __shared__ float4 s_gate[TILED ? DONE_WARPS : 1][TILED ? 64 : 1];      // vehicles inside the gate, per warp
+    __shared__ float4 s_ego[TILED ? DONE_WARPS : 1][TILED ? RPW : 1];      // the rows' ego circle centres
+    __shared__ int s_hit[TILED ? DONE_WARPS : 1][TILED ? RPW : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t tile = (int64_t)blockIdx.x * TILED_WARPS + warp;
+    const int64_t tile = (int64_t)blockIdx.x * DONE_WARPS + warp;
     int64_t i;
     bool owner = true, live = true;
     VehicleStream vs;
@@ -1710,7 +1715,7 @@ int launch_env_done(int task, const float *obs, int64_t ld, const float *act_sca
                     int v_light, int8_t *done, int64_t B, cudaStream_t st) {
     if (V > 0 && aligned16(obs + veh_off) && ld % 4 == 0) {
         const int64_t n_tiles = (B + RPW - 1) / RPW;
-        k_env_done<true><<<blocks_for(n_tiles, TILED_WARPS), TILED_WARPS * 32, 0, st>>>(
+        k_env_done<true><<<blocks_for(n_tiles, DONE_WARPS), DONE_WARPS * 32, 0, st>>>(
             make_dyn_consts(1.0 / 10.0), task, obs, ld, act_scaled, V, veh_off, v_light, done, B, DoneReset());
     } else {
         k_env_done<false><<<blocks_for(B, 128), 128, 0, st>>>(make_dyn_consts(1.0 / 10.0), task, obs, ld, act_scaled,
@@ -2099,7 +2104,7 @@ int ce2e_env_step_reset(const ce2e_paths *paths, int32_t *ref_idx, const float *
     if (V > 0 && aligned16(obs_out + veh_off) && ld_out % 4 == 0) {
         // done logic and the restart of the finished rows in ONE launch
         const int64_t n_tiles = (B + RPW - 1) / RPW;
-        k_env_done<true, true><<<blocks_for(n_tiles, TILED_WARPS), TILED_WARPS * 32, 0, st>>>(
+        k_env_done<true, true><<<blocks_for(n_tiles, DONE_WARPS), DONE_WARPS * 32, 0, st>>>(
             make_dyn_consts(1.0 / 10.0), paths->task, obs_out, ld_out, act_scaled_out, V, veh_off, v_light, done_out, B, X);
         return after_launch("k_env_done");
     }
