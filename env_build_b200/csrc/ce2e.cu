@@ -992,7 +992,10 @@ __global__ void k_ss(const float *__restrict__ obs, int64_t ld, const float *__r
 // of lane 2 * row + half at float4 index vehicle ^ (row % 4)), double buffered.  Needs a 16 B
 // aligned vehicle block and ld % 4 == 0.
 // ------------------------------------------------------------------------------------------
-constexpr int TILED_WARPS = 8;
+#ifndef CE2E_TILED_WARPS
+#define CE2E_TILED_WARPS 8
+#endif
+constexpr int TILED_WARPS = CE2E_TILED_WARPS;
 #ifndef CE2E_DONE_WARPS
 #define CE2E_DONE_WARPS 2
 #endif

@@ -192,6 +192,7 @@ def test_vehicle_selection(e2e, task):
         assert np.array_equal(res[i].view(np.int32), want.view(np.int32)), i
     # the single-env method with the reference's list-of-dicts format
     one = e2e.CrossroadEnd2end(task)
+    one.seed(17)
     one.reset()
     names = {c: r for c, r in zip(e2e.ROUTE_CLASSES, [('1o', '4i'), ('1o', '3i'), ('1o', '2i'), ('2o', '1i'), ('2o', '4i'),
                                                        ('2o', '3i'), ('3o', '2i'), ('3o', '1i'), ('3o', '4i'), ('4o', '3i'),
@@ -201,8 +202,11 @@ def test_vehicle_selection(e2e, task):
     one.all_vehicles = [dict(x=float(v[0]), y=float(v[1]), v=float(v[2]), phi=float(v[3]), route=names[e2e.ROUTE_CLASSES[c]])
                         for v, c in zip(veh[0], cls[0]) if c >= 0]
     ex, ey = one.obs.numpy()[0, 3:5]
-    want = orc.select_interested_vehicles(veh[0][cls[0] >= 0], cls[0][cls[0] >= 0], ex, ey, task)
-    assert np.array_equal(one._construct_veh_vector_short().view(np.int32), want.view(np.int32))
+    # (a reset leaves the virtual red-light vehicles on for one episode in ten, E2E:120-124: tell the oracle)
+    for virt1 in (one.virtual_red_light_vehicle, not one.virtual_red_light_vehicle):
+        one.virtual_red_light_vehicle = virt1
+        want = orc.select_interested_vehicles(veh[0][cls[0] >= 0], cls[0][cls[0] >= 0], ex, ey, task, int(one.v_light), virt1)
+        assert np.array_equal(one._construct_veh_vector_short().view(np.int32), want.view(np.int32))
 
 
 @pytest.mark.parametrize('V', [1, 5, 9, 32, 37])
@@ -353,6 +357,7 @@ def test_assigned_obs_is_adopted(e2e):
     rng = np.random.default_rng(1)
     task, B, V = 'left', 512, 8
     env = e2e.CrossroadEnd2end(task, num_envs=B)
+    env.seed(2)
     env.reset()
     ref = syn.make_ref_indexes(rng, B)
     obs = syn.make_obs(rng, B, task, V, env.ref_path.path_list, ref)
