@@ -315,7 +315,9 @@ def run_ours(args):
         out_all.record_stream(side)
         final.record_stream(side)
 
-    ke = max(3, min(K, 20))
+    # rollouts per timed e2e run (its own count, reported as e2e.steps): the run starts with an empty pipeline and
+    # ends drained, so fewer than 20 rollouts would mostly measure the fill
+    ke = max(20, min(K, 40))
     def join_streams():
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.current_stream().wait_stream(copy_s)
