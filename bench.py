@@ -332,19 +332,21 @@ def run_ours(args):
 
     # the same rollout through the other public entry, RolloutGraph (static device buffers, the 25 launches
     # replayed as one CUDA graph): load() from the pinned host buffers, run(), results back to pinned host
-    # buffers; two buffer sets so that H2D, kernels and D2H of consecutive rollouts overlap
-    graphs = [RolloutGraph(model, B, V, H) for _ in range(2)]
+    # buffers; three buffer sets so that H2D, kernels and D2H of consecutive rollouts overlap (2 / 3 / 4 sets measured:
+    # 1.085-1.099e9 / 1.104-1.106e9 / 1.087-1.110e9 on one box)
+    NSET = max(2, int(os.environ.get('CE2E_E2E_SETS', '3')))          # buffer sets of the e2e pipeline
+    graphs = [RolloutGraph(model, B, V, H) for _ in range(NSET)]
     for g_ in graphs:
         g_.load(obs, ref, tape)
         g_.run()
     torch.cuda.synchronize()
     gev = [dict(free=torch.cuda.Event(), ready=torch.cuda.Event(), done=torch.cuda.Event(), out=torch.cuda.Event())
-           for _ in range(2)]
+           for _ in range(NSET)]
     gcount = [0]
 
     def e2e_graph_step():
         main = torch.cuda.current_stream()
-        k = gcount[0] % 2
+        k = gcount[0] % NSET
         gcount[0] += 1
         g_, ev_ = graphs[k], gev[k]
         with torch.cuda.stream(copy_s):
@@ -656,7 +658,7 @@ def run_ours(args):
                 'e2e': {'value': e2e_graph['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': d2h, 'steps': ke,
                         'timing': 'one CUDA-event pair around all steps; H2D, kernels and D2H run on three streams '
-                                  '(two buffer sets), all joined before the end event; median of three such runs. The region '
+                                  '(three buffer sets), all joined before the end event; median of three such runs. The region '
                                   'starts with an empty pipeline and ends drained: the first H2D + rollout (1.4 ms) is not '
                                   'overlapped, after that a rollout costs its D2H (1.25 ms alone, ~1.35 ms under the '
                                   'concurrent H2D)',
